@@ -1,0 +1,178 @@
+/* sdr_b200 — C ABI of the B200 receive-chain library (libsdr_b200.so).
+ *
+ * Drop-in boundary for the block-based FM receive chain of TheZxc07/real-time-SDR.  The reference has
+ * no FFI layer: its boundary is a set of C++ free functions (include/filter.h, demod.h, pll.h,
+ * rds_utilities.h) and four thread bodies taking `args*` (include/rffrontend.h, mono.h, stereo.h, rds.h).
+ * real-time-sdr_b200/host/dy4_api.h re-declares exactly those C++ signatures and implements them on top
+ * of the entry points below; INTEGRATION.md shows the binding.  Every entry point cites the reference
+ * interface it replaces (paths relative to the reference repository root).
+ *
+ * Conventions: plain pointers and sizes only; every function returns an sdrb_status (0 = ok) and never
+ * terminates the process (the reference calls exit(1) on EOF, src/rffrontend.cpp:50-52).  Pointers named
+ * d_* are device pointers, h_* are host pointers.  `stream` arguments are CUDA streams passed as void*
+ * (NULL = the default stream).  All batched arrays are stream-major: row s starts at base + s*pitch
+ * (pitch in ELEMENTS of the array's type).
+ */
+#ifndef SDR_B200_H
+#define SDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDRB_TAPS 101 /* rf_taps, src/project.cpp:34 */
+
+typedef enum {
+    SDRB_OK = 0,
+    SDRB_ERR_INVALID = 1,   /* bad argument / unsupported configuration */
+    SDRB_ERR_CUDA = 2,      /* a CUDA call failed; sdrb_last_error() has the text */
+    SDRB_ERR_NO_DEVICE = 3, /* no usable GPU: there is no CPU fallback */
+    SDRB_ERR_STATE = 4      /* call order violated (e.g. reading results before a block was processed) */
+} sdrb_status;
+
+const char* sdrb_last_error(void);
+int sdrb_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. Tap designers (host, init time).  Bit-exact replacements for
+ *    impulseResponseLPF/BPF/APF/RRC, include/filter.h:18-23, src/filter.cpp:13-102.
+ * ------------------------------------------------------------------------------------------------ */
+int sdrb_design_lpf(float Fs, float Fc, int num_taps, float* h);              /* filter.h:18 */
+int sdrb_design_lpf_gain(float Fs, float Fc, int num_taps, int u, float* h);  /* filter.h:19 */
+int sdrb_design_bpf(float Fs, float f_lo, float f_hi, int num_taps, float* h);/* filter.h:21 */
+int sdrb_design_apf(float gain, int num_taps, float* h);                      /* filter.h:22 */
+int sdrb_design_rrc(float Fs, int num_taps, float* h);                        /* filter.h:23 */
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Batched stage primitives on device memory.  Each processes ONE block for n_streams independent
+ *    streams and carries the same state the reference function carries, but as explicit arrays.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* convolveFIR(y, x, h, state, decim) — include/filter.h:20, src/filter.cpp:106-121.
+ * d_x [n_streams][x_pitch] (nx samples used), d_state [n_streams][nh-1] in/out, d_y [n_streams][y_pitch]
+ * receives nx/decim samples.  nh <= 128. */
+int sdrb_fir_decim(const float* d_x, size_t x_pitch, int nx, const float* h_taps, int nh, float* d_state,
+                   float* d_y, size_t y_pitch, int decim, int n_streams, void* stream);
+
+/* convolveFIR(y, x, h, state, up, down) — include/filter.h:24, src/filter.cpp:123-147.
+ * h_taps holds the full prototype (nh = 101*up at every reference call site); d_state [n_streams][nstate]
+ * with nstate = (nh-1)/up; d_y receives nx*up/down samples. */
+int sdrb_fir_updown(const float* d_x, size_t x_pitch, int nx, const float* h_taps, int nh, float* d_state,
+                    int nstate, float* d_y, size_t y_pitch, int up, int down, int n_streams, void* stream);
+
+/* fmDemodNoArctan(I, Q, prev_I, prev_Q, out) — include/demod.h:5-6, src/demod.cpp:3-24.
+ * d_prev [n_streams][2] = {prev_I, prev_Q} in/out. */
+int sdrb_fm_demod(const float* d_I, const float* d_Q, size_t iq_pitch, int n, float* d_prev, float* d_out,
+                  size_t out_pitch, int n_streams, void* stream);
+
+/* fmpll(in, freq, Fs, out, state, ncoScale, phaseAdjust, normBandwidth) — include/pll.h:10-20,
+ * src/pll.cpp:4-61.  State mirrors pllblock_args; `last_out` is the element the reference keeps in
+ * pllOut[N] between calls (src/pll.cpp:18).  d_out [n_streams][out_pitch] receives N+1 samples. */
+typedef struct {
+    float feedbackI, feedbackQ, integrator, phaseEst;
+    double trigOffset;
+    float lastCarrier;
+    float last_out;
+} sdrb_pll_state;
+int sdrb_pll(const float* d_in, size_t in_pitch, int n, float freq, float Fs, float ncoScale, float phaseAdjust,
+             float normBandwidth, sdrb_pll_state* d_state, float* d_out, size_t out_pitch, int n_streams,
+             void* stream);
+
+/* cdr(sps, signal) — include/rds_utilities.h:6, src/rds_utilities.cpp:4-21.  d_offset [n_streams]. */
+int sdrb_cdr(const float* d_x, size_t x_pitch, int n, int sps, int* d_offset, int n_streams, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. The fused receive chain: RF_frontend + mono|stereo + rds for n_streams stations
+ *    (include/rffrontend.h:5, mono.h:5, stereo.h:4, rds.h:4; struct args, include/args.h:6-19).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    /* mirrors struct args, include/args.h:6-19 */
+    int rf_Fs, rf_Fc, rf_taps, rf_decim;
+    int audio_decim, audio_upsample;
+    int if_Fs, audio_Fc, audio_Fs, symbol_Fs;
+    int rds_on;
+    /* which audio thread body runs: 'm' = mono(), 's'/'r' = stereo() (src/project.cpp:111-132) */
+    int type;
+    /* batch */
+    int n_streams;
+    int device;         /* CUDA device ordinal */
+    int keep_stages;    /* 1: keep every intermediate addressable through sdrb_chain_stage (parity tests) */
+    int always_rds_dsp; /* 1: run the RDS DSP even when rds_on == 0, as the reference binary does (src/project.cpp:134) */
+} sdrb_config;
+
+/* Fills cfg from the reference's mode table (src/project.cpp:31-44,67-108) and type switch (:111-132). */
+int sdrb_config_for_mode(int mode, int type, int n_streams, sdrb_config* cfg);
+
+typedef struct sdrb_chain sdrb_chain;
+
+typedef struct {
+    int block_pairs;   /* IQ pairs per block per stream (src/rffrontend.cpp:21) */
+    int block_bytes;   /* 2*block_pairs */
+    int if_block;      /* IF-rate samples per block (src/mono.cpp:19) */
+    int audio_block;   /* audio frames per block */
+    int pcm_per_block; /* int16 samples per block per stream: audio_block (mono) or 2*audio_block */
+    int rds_block;     /* RDS-rate samples per block (if_block*247/640) */
+    int max_bits;      /* capacity of the per-block bit record */
+    int max_groups;    /* capacity of the per-block group record */
+} sdrb_chain_info;
+
+int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out);
+int sdrb_chain_destroy(sdrb_chain* c);
+int sdrb_chain_get_info(const sdrb_chain* c, sdrb_chain_info* info);
+
+/* One block for every stream, input already in device memory: d_iq [n_streams][iq_pitch] bytes,
+ * interleaved I,Q,I,Q (src/rffrontend.cpp:48,58-63).  Asynchronous: work is enqueued on the chain's own
+ * CUDA streams; results are valid after sdrb_chain_sync() or when read through the calls below. */
+int sdrb_chain_process_device(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch);
+
+/* Same, from host memory (pinned memory recommended).  The H2D copy is part of the call and is
+ * overlapped with the previous block's kernels. */
+int sdrb_chain_process_host(sdrb_chain* c, const uint8_t* h_iq, size_t iq_pitch);
+
+int sdrb_chain_sync(sdrb_chain* c);
+
+/* Results of the most recent block.
+ * pcm: [n_streams][pcm_pitch] int16, what mono()/stereo() fwrite to stdout (src/mono.cpp:40-45,
+ *      src/stereo.cpp:100-111): L on even, R on odd indices for stereo. */
+int sdrb_chain_read_pcm(sdrb_chain* c, int16_t* h_pcm, size_t pcm_pitch);
+int sdrb_chain_pcm_device(sdrb_chain* c, const int16_t** d_pcm, size_t* pcm_pitch);
+
+/* Per-block RDS record (src/rds.cpp:135-189). */
+typedef struct {
+    int32_t cdr_offset;  /* -1 while the decoder is gated (block_count <= 5 or !rds_on) */
+    int32_t n_symbols;
+    int32_t n_bits;
+    int32_t n_groups;    /* groups completed by this block's frame sync (0 except every 15th decode block) */
+    uint8_t bits[48];    /* differentially decoded bits of this block */
+    uint64_t groups[8];  /* 64-bit group registers A|B|C|D as handed to parse() (src/rds_utilities.cpp:172) */
+} sdrb_rds_record;
+int sdrb_chain_read_rds(sdrb_chain* c, sdrb_rds_record* h_records /* [n_streams] */);
+
+/* parse() — src/rds_utilities.cpp:172-199: the text the reference prints on stderr for one group.
+ * chars/output are the caller-held PS assembly state (src/rds.cpp:68-69).  Returns bytes written. */
+int sdrb_rds_parse(uint64_t group, uint64_t* chars, uint64_t* output, char* text, int text_cap);
+
+/* Intermediates of the most recent block (keep_stages = 1 only).  Names: fm_demod pilot carrier stereo_band
+ * mono_filt stereo_filt audio_filt rds_band gen_pilot IPLL rds_filt rds_clean.  Copies `count` floats per
+ * stream into h_out [n_streams][count]; *count is set to the per-stream length. */
+int sdrb_chain_stage(sdrb_chain* c, const char* name, float* h_out, int cap_per_stream, int* count);
+
+/* Carried state (checkpoint/resume): opaque blob, size via sdrb_chain_state_bytes. */
+size_t sdrb_chain_state_bytes(const sdrb_chain* c);
+int sdrb_chain_state_save(sdrb_chain* c, void* h_blob);
+int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob);
+
+/* Device time of the kernels of the most recent block, by kernel family, in milliseconds (CUDA events).
+ * names/ms arrays of capacity cap; returns the count in *n. */
+int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int cap, int* n);
+int sdrb_chain_set_profiling(sdrb_chain* c, int on);
+/* Number of kernels launched by this chain so far. */
+long long sdrb_chain_launch_count(const sdrb_chain* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDR_B200_H */

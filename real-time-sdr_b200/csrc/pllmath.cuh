@@ -1,0 +1,371 @@
+// Correctly-rounded float <- double-libm emulation for the PLL (host + device).
+//
+// The reference PLL (/root/reference/src/pll.cpp:39,49,50,52) calls glibc's DOUBLE atan2/cos/sin on
+// float arguments and stores the result in a float.  Its NCO phase lives in a float that grows without
+// bound, so one different last bit anywhere in the loop changes the audio for good.
+// What has to be reproduced is therefore the function  float -> RN_float(RN_double(f(x))).
+//
+// Every function here works in two tiers:
+//   fast : plain double arithmetic with a proven error of a few double ulps (own range reduction, so
+//          the unbounded NCO phase never hits a slow library path); the result is accepted unless it
+//          lies within kAmbigUlps double-ulps of a float rounding boundary (probability ~1e-6);
+//   slow : double-double arithmetic (~2^-100), which decides those cases.
+// Both tiers are pure IEEE +,-,*,/,fma, so the host build of this header (tests/, no GPU needed) and
+// the sm_100a build produce the same values.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define SDRB_HD __host__ __device__ __forceinline__
+#else
+#define SDRB_HD inline
+#endif
+
+namespace sdrb {
+namespace cr {
+
+// ---- exact float ops: never contracted into FMA (the reference build has no FMA) ----
+SDRB_HD float fmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;  // host builds also use -ffp-contract=off; volatile is belt and braces
+    return r;
+#endif
+}
+SDRB_HD float fadd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
+}
+SDRB_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+SDRB_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+SDRB_HD double dfma(double a, double b, double c) { return fma(a, b, c); }
+
+SDRB_HD uint64_t dbits(double v) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(v);
+#else
+    uint64_t b;
+    memcpy(&b, &v, 8);
+    return b;
+#endif
+}
+
+// ---- double-double ----
+struct dd {
+    double hi, lo;
+};
+SDRB_HD dd two_sum(double a, double b) {
+    double s = dadd(a, b);
+    double bb = dadd(s, -a);
+    double e = dadd(dadd(a, -dadd(s, -bb)), dadd(b, -bb));
+    return dd{s, e};
+}
+SDRB_HD dd fast_two_sum(double a, double b) {  // |a| >= |b|
+    double s = dadd(a, b);
+    double e = dadd(b, -dadd(s, -a));
+    return dd{s, e};
+}
+SDRB_HD dd two_prod(double a, double b) {
+    double p = dmul(a, b);
+    return dd{p, dfma(a, b, -p)};
+}
+SDRB_HD dd dd_add(dd a, dd b) {
+    dd s = two_sum(a.hi, b.hi);
+    dd t = two_sum(a.lo, b.lo);
+    s.lo = dadd(s.lo, t.hi);
+    s = fast_two_sum(s.hi, s.lo);
+    s.lo = dadd(s.lo, t.lo);
+    return fast_two_sum(s.hi, s.lo);
+}
+SDRB_HD dd dd_add_d(dd a, double b) {
+    dd s = two_sum(a.hi, b);
+    s.lo = dadd(s.lo, a.lo);
+    return fast_two_sum(s.hi, s.lo);
+}
+SDRB_HD dd dd_neg(dd a) { return dd{-a.hi, -a.lo}; }
+SDRB_HD dd dd_mul(dd a, dd b) {
+    dd p = two_prod(a.hi, b.hi);
+    p.lo = dadd(p.lo, dadd(dmul(a.hi, b.lo), dmul(a.lo, b.hi)));
+    return fast_two_sum(p.hi, p.lo);
+}
+SDRB_HD dd dd_div_d(dd a, double d) {
+    double q1 = a.hi / d;
+    dd p = two_prod(q1, d);
+    double rem = dadd(dadd(dadd(a.hi, -p.hi), -p.lo), a.lo);
+    double q2 = rem / d;
+    return fast_two_sum(q1, q2);
+}
+SDRB_HD dd dd_div(dd a, dd b) {
+    double q1 = a.hi / b.hi;
+    dd r = dd_add(a, dd_neg(dd_mul(b, dd{q1, 0.0})));
+    double q2 = r.hi / b.hi;
+    r = dd_add(r, dd_neg(dd_mul(b, dd{q2, 0.0})));
+    double q3 = r.hi / b.hi;
+    dd q = fast_two_sum(q1, q2);
+    return dd_add_d(q, q3);
+}
+
+// ---- float rounding boundary test ----
+// A double v rounds to float by dropping its low 29 mantissa bits; the boundary (tie) pattern of those
+// bits is 0x10000000.  `true` means: v is so close to a boundary (or so small that the float is
+// subnormal and the pattern does not apply) that a few-ulp error in v could change the float.
+constexpr uint32_t kAmbigUlps = 256;
+SDRB_HD bool near_float_boundary(double v) {
+    uint64_t b = dbits(v);
+    uint32_t e = (uint32_t)(b >> 52) & 0x7FFu;
+    if (e == 0 && (b << 1) == 0) return false;      // exact zero
+    if (e < 1023u - 126u + 1u) return true;         // float-subnormal range: let the slow tier decide
+    uint32_t low = (uint32_t)b & 0x1FFFFFFFu;
+    uint32_t dist = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
+    return dist <= kAmbigUlps;
+}
+
+// ---- pi/2 in pieces (generated with mpmath, tests/gen_pllmath_consts.py) ----
+// P1..P5 carry 22 significant bits each, so k*Pi is exact in double for |k| < 2^31.
+constexpr double kTwoOverPi = 0x1.45f306dc9c883p-1;
+constexpr double kP1 = 0x1.921fb00000000p+0;
+constexpr double kP2 = 0x1.5110b00000000p-22;
+constexpr double kP3 = 0x1.1846980000000p-44;
+constexpr double kP4 = 0x1.3198a00000000p-69;
+constexpr double kP5 = 0x1.701b800000000p-92;
+constexpr double kPTailHi = 0x1.cd129024e088ap-115;
+constexpr double kPTailLo = 0x1.9f31d0082efaap-169;
+constexpr double kP4Rest = 0x1.3198a2e037073p-69;  // pi/2 - P1 - P2 - P3 rounded to 53 bits
+constexpr double kPiH = 0x1.921fb54442d18p+1, kPiM = 0x1.1a62633145c07p-53, kPiL = -0x1.f1976b7ed8fbcp-109;
+constexpr double kPio2H = 0x1.921fb54442d18p+0, kPio2M = 0x1.1a62633145c07p-54, kPio2L = -0x1.f1976b7ed8fbcp-110;
+constexpr double kReduceLimit = 3.0e9;  // |x| below this: k < 2^31, exact Cody-Waite steps
+
+// ---- sin / cos ----
+// fast tier: x - k*pi/2 with four fma steps.  Steps 1 and 2 are exact (x is a float, k*P1 and k*P2
+// are exact and the differences fit in 53 bits); step 3 is exact whenever |r| < 2^-12 and otherwise
+// rounds with relative error 2^-53; step 4 adds k*2^-122 absolute.  |r| stays >= 2^-30 for every
+// float below kReduceLimit (checked exhaustively, tests/test_pllmath.py), so r is good to ~2^-53
+// relative; the callers still send |r| < 2^-30 to the slow tier.
+SDRB_HD void sincos_fast(double x, double& s, double& c, bool& tiny) {
+    double kd = rint(dmul(x, kTwoOverPi));
+    double r = dfma(-kd, kP1, x);
+    r = dfma(-kd, kP2, r);
+    r = dfma(-kd, kP3, r);
+    r = dfma(-kd, kP4Rest, r);
+    tiny = (kd != 0.0) && fabs(r) < 0x1p-30;  // kd == 0: r = x exactly
+    double z = dmul(r, r);
+    double z2 = dmul(z, z), z4 = dmul(z2, z2);
+    // sin r = r + r z (S1 + S2 z + ... + S8 z^7),  Sj = (-1)^j / (2j+1)!   (Taylor through r^17)
+    double sa = dfma(0x1.1111111111111p-7, z, -0x1.5555555555555p-3);    //  1/120, -1/6
+    double sb = dfma(0x1.71de3a556c734p-19, z, -0x1.a01a01a01a01ap-13);  //  1/362880, -1/5040
+    double sc = dfma(0x1.6124613a86d09p-33, z, -0x1.ae64567f544e4p-26);  //  1/6227020800, -1/39916800
+    double sd = dfma(0x1.952c77030ad4ap-49, z, -0x1.ae7f3e733b81fp-41);  //  1/355687428096000, -1/1307674368000
+    double sp = dfma(dfma(sd, z2, sc), z4, dfma(sb, z2, sa));
+    double sr = dfma(dmul(r, z), sp, r);
+    // cos r = 1 - z/2 + z^2 (C2 + C3 z + ... + C9 z^7),  Cj = (-1)^j / (2j)!   (Taylor through r^18)
+    double ca = dfma(-0x1.6c16c16c16c17p-10, z, 0x1.5555555555555p-5);   // -1/720, 1/24
+    double cb = dfma(-0x1.27e4fb7789f5cp-22, z, 0x1.a01a01a01a01ap-16);  // -1/3628800, 1/40320
+    double cc = dfma(-0x1.93974a8c07c9dp-37, z, 0x1.1eed8eff8d898p-29);  // -1/87178291200, 1/479001600
+    double cd = dfma(-0x1.6827863b97d97p-53, z, 0x1.ae7f3e733b81fp-45);  // -1/6402373705728000, 1/20922789888000
+    double cp = dfma(dfma(cd, z2, cc), z4, dfma(cb, z2, ca));
+    double cr_ = dfma(z2, cp, dfma(-0.5, z, 1.0));
+    int q = (int)((long long)kd & 3);
+    double ss = (q & 1) ? cr_ : sr;
+    double cs = (q & 1) ? sr : cr_;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cs : cs;
+}
+
+// slow tier: the same k, the reduction carried in double-double with pi/2 to ~170 bits, Taylor series
+// in double-double.  Returns RN_double(sin x), RN_double(cos x) up to ~2^-100.
+SDRB_HD void sincos_slow(double x, double& s, double& c) {
+    double kd = rint(dmul(x, kTwoOverPi));
+    double r2 = dfma(-kd, kP2, dfma(-kd, kP1, x));  // exact, see above
+    dd r = dd_add_d(dd{r2, 0.0}, -dmul(kd, kP3));   // products with the 22-bit pieces are exact
+    r = dd_add_d(r, -dmul(kd, kP4));
+    r = dd_add_d(r, -dmul(kd, kP5));
+    r = dd_add(r, dd_neg(two_prod(kd, kPTailHi)));
+    r = dd_add_d(r, -dmul(kd, kPTailLo));
+    dd z = dd_mul(r, r);
+    dd ts = r, ssum = r;            // sin terms r^(2j+1)/(2j+1)!
+    dd tc = dd{1.0, 0.0}, csum = tc;  // cos terms r^(2j)/(2j)!
+    for (int j = 1; j <= 15; j++) {
+        tc = dd_div_d(dd_mul(tc, z), (double)((2 * j - 1) * (2 * j)));
+        ts = dd_div_d(dd_mul(ts, z), (double)((2 * j) * (2 * j + 1)));
+        if (j & 1) {
+            csum = dd_add(csum, dd_neg(tc));
+            ssum = dd_add(ssum, dd_neg(ts));
+        } else {
+            csum = dd_add(csum, tc);
+            ssum = dd_add(ssum, ts);
+        }
+    }
+    int q = (int)((long long)kd & 3);
+    double ss = (q & 1) ? csum.hi : ssum.hi;
+    double cs = (q & 1) ? ssum.hi : csum.hi;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cs : cs;
+}
+
+// (float)sin((double)t), (float)cos((double)t) as glibc + the C++ float conversion produce them.
+SDRB_HD void sincos_f(float t, float& s, float& c) {
+    double x = (double)t;
+    if (!(fabs(x) < kReduceLimit)) {  // also NaN/Inf: no own reduction, defer to the library
+        s = (float)sin(x);
+        c = (float)cos(x);
+        return;
+    }
+    if (t == 0.0f) {  // keeps the sign of zero: sin(-0) = -0
+        s = t;
+        c = 1.0f;
+        return;
+    }
+    double ds, dc;
+    bool tiny;
+    sincos_fast(x, ds, dc, tiny);
+    if (tiny || near_float_boundary(ds) || near_float_boundary(dc)) sincos_slow(x, ds, dc);
+    s = (float)ds;
+    c = (float)dc;
+}
+SDRB_HD float cos_f(float t) {
+    double x = (double)t;
+    if (!(fabs(x) < kReduceLimit)) return (float)cos(x);
+    double ds, dc;
+    bool tiny;
+    sincos_fast(x, ds, dc, tiny);
+    if (tiny || near_float_boundary(dc)) sincos_slow(x, ds, dc);
+    return (float)dc;
+}
+
+// ---- atan2 ----
+// atan(i/16), i = 0..16, as double-double (mpmath).
+struct AtanTab {
+    double hi[17], lo[17];
+};
+#define SDRB_ATAN_TAB_INIT                                                                                          \
+    {{0x0.0p+0, 0x1.ff55bb72cfdeap-5, 0x1.fd5ba9aac2f6ep-4, 0x1.7b97b4bce5b02p-3, 0x1.f5b75f92c80ddp-3,              \
+      0x1.362773707ebccp-2, 0x1.6f61941e4def1p-2, 0x1.a64eec3cc23fdp-2, 0x1.dac670561bb4fp-2, 0x1.0657e94db30d0p-1, \
+      0x1.1e00babdefeb4p-1, 0x1.345f01cce37bbp-1, 0x1.4978fa3269ee1p-1, 0x1.5d58987169b18p-1, 0x1.700a7c5784634p-1, \
+      0x1.819d0b7158a4dp-1, 0x1.921fb54442d18p-1},                                                                   \
+     {0x0.0p+0, -0x1.c934d86d23f1dp-60, -0x1.cd37686760c17p-59, 0x1.347b0b4f881cap-58, 0x1.8ab6e3cf7afbdp-57,        \
+      -0x1.963a544b672d8p-57, -0x1.c63aae6f6e918p-56, -0x1.24dec1b50b7ffp-56, 0x1.a2b7f222f65e2p-56,                 \
+      -0x1.d5b495f6349e6p-56, -0x1.928df287a668fp-58, 0x1.1021137c71102p-55, 0x1.2419a87f2a458p-56,                  \
+      0x1.0028e4bc5e7cap-57, -0x1.8c34d25aadef6p-56, -0x1.bf76229d3b917p-56, 0x1.1a62633145c07p-55}}
+
+// Reduced problem shared by both tiers: atan(num0/den0), 0 <= num0 <= den0, via
+//   atan(t) = atan(c) + atan((num0 - c den0)/(den0 + c num0)),  c = i/16 nearest to t.
+// num0 and den0 are floats held in doubles, c has 5 bits, so both linear combinations are exact.
+struct AtanRed {
+    int i;
+    double nn, dn;
+};
+SDRB_HD AtanRed atan_reduce(double num0, double den0) {
+    float est = (float)num0 / (float)den0;  // any estimate within ~1e-3 of t works
+    int i = (int)(est * 16.0f + 0.5f);
+    i = i < 0 ? 0 : (i > 16 ? 16 : i);
+    double c = (double)i * 0.0625;
+    return AtanRed{i, dfma(-c, den0, num0), dfma(c, num0, den0)};
+}
+
+SDRB_HD double atan2_fast(double ax, double ay, bool xneg, const AtanTab& tab) {
+    bool swap = ay > ax;
+    AtanRed rd = atan_reduce(swap ? ax : ay, swap ? ay : ax);
+    double z = rd.nn / rd.dn;
+    double z2 = dmul(z, z), z4 = dmul(z2, z2);
+    // atan z = z + z z2 (A1 + A2 z2 + ... + A5 z2^4), Aj = (-1)^j/(2j+1); |z| <= 1/32 + eps
+    double pa = dfma(0x1.999999999999ap-3, z2, -0x1.5555555555555p-2);   //  1/5, -1/3
+    double pb = dfma(0x1.c71c71c71c71cp-4, z2, -0x1.2492492492492p-3);   //  1/9, -1/7
+    double poly = dfma(z4, dfma(-0x1.745d1745d1746p-4, z4, pb), pa);  // pa + z4*(pb + z4*A5)
+    double at = dfma(dmul(z, z2), poly, z);
+    double res = dadd(tab.hi[rd.i], dadd(tab.lo[rd.i], at));
+    if (swap) res = dadd(dadd(kPio2H, -res), kPio2M);
+    if (xneg) res = dadd(dadd(kPiH, -res), kPiM);
+    return res;
+}
+
+SDRB_HD double atan2_slow(double ax, double ay, bool xneg, const AtanTab& tab) {
+    bool swap = ay > ax;
+    AtanRed rd = atan_reduce(swap ? ax : ay, swap ? ay : ax);
+    dd z = dd_div(dd{rd.nn, 0.0}, dd{rd.dn, 0.0});
+    dd z2 = dd_mul(z, z);
+    dd term = z, sum = z;
+    for (int j = 1; j <= 13; j++) {  // |z|^27/27 < 2^-130
+        term = dd_mul(term, z2);
+        dd t = dd_div_d(term, (double)(2 * j + 1));
+        sum = (j & 1) ? dd_add(sum, dd_neg(t)) : dd_add(sum, t);
+    }
+    dd res = dd_add(dd{tab.hi[rd.i], tab.lo[rd.i]}, sum);
+    if (swap) res = dd_add_d(dd_add(dd{kPio2H, kPio2M}, dd_neg(res)), kPio2L);
+    if (xneg) res = dd_add_d(dd_add(dd{kPiH, kPiM}, dd_neg(res)), kPiL);
+    return res.hi;
+}
+
+// (float)atan2((double)y, (double)x) as glibc + the float conversion produce it.
+SDRB_HD float atan2_f(float yf, float xf, const AtanTab& tab) {
+    const float kPiF = 3.14159274101257324f, kPio2F = 1.57079637050628662f;  // (float)pi, (float)(pi/2)
+    if (yf != yf || xf != xf || fabsf(yf) == INFINITY || fabsf(xf) == INFINITY)
+        return (float)atan2((double)yf, (double)xf);
+    if (yf == 0.0f) {  // atan2(+-0, x): +-0 for x > 0 or +0, +-pi for x < 0 or -0
+        bool xn = signbit(xf);
+        return xn ? copysignf(kPiF, yf) : yf;
+    }
+    if (xf == 0.0f) return copysignf(kPio2F, yf);
+    double ax = fabs((double)xf), ay = fabs((double)yf);
+    bool xneg = xf < 0.0f;
+    double v = atan2_fast(ax, ay, xneg, tab);
+    if (near_float_boundary(v)) v = atan2_slow(ax, ay, xneg, tab);
+    float r = (float)v;
+    return yf < 0.0f ? -r : r;
+}
+
+// ---- one PLL sample, /root/reference/src/pll.cpp:34-53 ----
+struct PllCoef {
+    float Kp, Ki;       // :8-9
+    double w;           // (2*PI) * (double)(freq/Fs), the loop-invariant head of :47
+    float ncoScale, phaseAdjust;
+};
+struct PllState {
+    float feedbackI, feedbackQ, integrator, phaseEst;
+    double trigOffset;
+};
+SDRB_HD PllCoef pll_coef(float freq, float Fs, float ncoScale, float phaseAdjust, float normBandwidth) {
+    const float Cp = 2.666f, Ci = 3.555f;
+    PllCoef c;
+    c.Kp = fmul(normBandwidth, Cp);
+    c.Ki = fmul(fmul(normBandwidth, normBandwidth), Ci);
+    c.w = dmul(2 * 3.14159265358979323846, (double)(freq / Fs));
+    c.ncoScale = ncoScale;
+    c.phaseAdjust = phaseAdjust;
+    return c;
+}
+SDRB_HD float pll_step(float in, PllState& st, const PllCoef& k, const AtanTab& tab) {
+    float errorI = fmul(in, st.feedbackI);
+    float errorQ = fmul(in, -st.feedbackQ);
+    float errorD = atan2_f(errorQ, errorI, tab);
+    st.integrator = fadd(st.integrator, fmul(k.Ki, errorD));
+    st.phaseEst = fadd(fadd(st.phaseEst, fmul(k.Kp, errorD)), st.integrator);
+    st.trigOffset = dadd(st.trigOffset, 1.0);
+    float trigArg = (float)dadd(dmul(k.w, st.trigOffset), (double)st.phaseEst);
+    sincos_f(trigArg, st.feedbackQ, st.feedbackI);
+    return cos_f(fadd(fmul(trigArg, k.ncoScale), k.phaseAdjust));
+}
+
+}  // namespace cr
+}  // namespace sdrb

@@ -1,0 +1,116 @@
+// Host build of real-time-sdr_b200/csrc/pllmath.cuh for the CPU test-suite (no GPU needed).
+// Exposes the correctly-rounded trig tiers and scan helpers that compare them with this machine's
+// glibc, i.e. with what the reference build computes ((float)sin((double)x) etc.).
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../real-time-sdr_b200/csrc/pllmath.cuh"
+
+using namespace sdrb::cr;
+static const AtanTab kTab = SDRB_ATAN_TAB_INIT;
+
+static float bits2f(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+static uint32_t f2bits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
+
+extern "C" {
+
+void crh_sincos(const float* t, int n, float* s, float* c) { for (int i = 0; i < n; i++) sincos_f(t[i], s[i], c[i]); }
+void crh_cos(const float* t, int n, float* c) { for (int i = 0; i < n; i++) c[i] = cos_f(t[i]); }
+void crh_atan2(const float* y, const float* x, int n, float* o) { for (int i = 0; i < n; i++) o[i] = atan2_f(y[i], x[i], kTab); }
+
+// force a tier: 0 fast only (no boundary check), 1 slow only
+void crh_sincos_tier(const float* t, int n, int tier, float* s, float* c) {
+    for (int i = 0; i < n; i++) {
+        double ds, dc; bool tiny;
+        if (tier == 0) sincos_fast((double)t[i], ds, dc, tiny); else sincos_slow((double)t[i], ds, dc);
+        s[i] = (float)ds; c[i] = (float)dc;
+    }
+}
+void crh_atan2_tier(const float* y, const float* x, int n, int tier, float* o) {
+    for (int i = 0; i < n; i++) {
+        double ax = fabs((double)x[i]), ay = fabs((double)y[i]);
+        double v = tier == 0 ? atan2_fast(ax, ay, x[i] < 0, kTab) : atan2_slow(ax, ay, x[i] < 0, kTab);
+        float r = (float)v; o[i] = y[i] < 0 ? -r : r;
+    }
+}
+
+// Scan float bit patterns [lo, hi) with the given stride; compare sincos_f with glibc.
+// out[0] mismatches sin, out[1] mismatches cos, out[2] slow-tier entries, out[3] first bad pattern,
+// out[4] = min |r| seen as float bits of (float)|r| (for the reduction bound), out[5] count
+void crh_scan_sincos(uint32_t lo, uint32_t hi, uint32_t stride, int nthreads, uint64_t* out) {
+    std::atomic<uint64_t> bad_s{0}, bad_c{0}, slow{0}, first{0}, cnt{0};
+    std::vector<double> minr(nthreads, 1.0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([&, t]() {
+            uint64_t bs = 0, bc = 0, sl = 0, n = 0; double mr = 1.0;
+            for (uint64_t b = (uint64_t)lo + (uint64_t)t * stride; b < hi; b += (uint64_t)stride * nthreads) {
+                float x = bits2f((uint32_t)b);
+                float s, c; sincos_f(x, s, c);
+                float rs = (float)sin((double)x), rc = (float)cos((double)x);
+                if (f2bits(s) != f2bits(rs)) { bs++; if (!first) first = b; }
+                if (f2bits(c) != f2bits(rc)) { bc++; if (!first) first = b; }
+                double ds, dc; bool tiny; sincos_fast((double)x, ds, dc, tiny);
+                if (tiny || near_float_boundary(ds) || near_float_boundary(dc)) sl++;
+                double kd = rint((double)x * kTwoOverPi);
+                if (kd != 0) { double r = fabs(fmin(fabs(ds), fabs(dc))); if (r < mr) mr = r; }
+                n++;
+            }
+            bad_s += bs; bad_c += bc; slow += sl; cnt += n; minr[t] = mr;
+        });
+    for (auto& x : th) x.join();
+    double mr = 1.0; for (double v : minr) if (v < mr) mr = v;
+    out[0] = bad_s; out[1] = bad_c; out[2] = slow; out[3] = first; memcpy(&out[4], &mr, 8); out[5] = cnt;
+}
+
+// Random (y, x) pairs from a 64-bit LCG seeded per thread; mode 0: arbitrary floats with exponents in a
+// band, mode 1: PLL-like (y = in*-sin, x = in*cos).  out[0] mismatches, out[1] slow entries, out[2] count
+void crh_scan_atan2(uint64_t seed, uint64_t n_per_thread, int mode, int nthreads, uint64_t* out) {
+    std::atomic<uint64_t> bad{0}, slow{0}, cnt{0}, firsty{0}, firstx{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([&, t]() {
+            uint64_t s = seed * 0x9E3779B97F4A7C15ull + (uint64_t)t * 0xD1B54A32D192ED03ull + 1;
+            auto next = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 32); };
+            uint64_t b = 0, sl = 0;
+            for (uint64_t i = 0; i < n_per_thread; i++) {
+                float y, x;
+                if (mode == 0) {
+                    uint32_t a = next(), c = next();
+                    // sign | exponent in [100, 140] | mantissa
+                    y = bits2f((a & 0x807FFFFFu) | ((100u + (a >> 23) % 41u) << 23));
+                    x = bits2f((c & 0x807FFFFFu) | ((100u + (c >> 23) % 41u) << 23));
+                } else {
+                    float in = bits2f((next() & 0x807FFFFFu) | ((110u + next() % 17u) << 23));
+                    float th_ = (float)(next() * (3.0e6 / 4294967296.0));
+                    float fs = (float)sin((double)th_), fc = (float)cos((double)th_);
+                    y = in * -fs; x = in * fc;
+                }
+                float r = atan2_f(y, x, kTab);
+                float g = (float)atan2((double)y, (double)x);
+                if (f2bits(r) != f2bits(g)) { b++; if (!firsty) { firsty = f2bits(y); firstx = f2bits(x); } }
+                if (y != 0 && x != 0) {
+                    double v = atan2_fast(fabs((double)x), fabs((double)y), x < 0, kTab);
+                    if (near_float_boundary(v)) sl++;
+                }
+            }
+            bad += b; slow += sl; cnt += n_per_thread;
+        });
+    for (auto& x : th) x.join();
+    out[0] = bad; out[1] = slow; out[2] = cnt; out[3] = firsty; out[4] = firstx;
+}
+
+// The PLL loop built from pll_step; same calling convention as the reference's fmpll.
+void crh_pll(const float* in, int n, float freq, float Fs, float scale, float adjust, float bw, float* out,
+             float* st4, double* trig) {
+    PllCoef k = pll_coef(freq, Fs, scale, adjust, bw);
+    PllState st{st4[0], st4[1], st4[2], st4[3], *trig};
+    out[0] = out[n];
+    for (int i = 0; i < n; i++) out[i + 1] = pll_step(in[i], st, k, kTab);
+    st4[0] = st.feedbackI; st4[1] = st.feedbackQ; st4[2] = st.integrator; st4[3] = st.phaseEst; *trig = st.trigOffset;
+}
+}
