@@ -100,7 +100,6 @@ typedef struct {
     int n_streams;
     int device;         /* CUDA device ordinal */
     int keep_stages;    /* 1: keep every intermediate addressable through sdrb_chain_stage (parity tests) */
-    int always_rds_dsp; /* 1: run the RDS DSP even when rds_on == 0, as the reference binary does (src/project.cpp:134) */
 } sdrb_config;
 
 /* Fills cfg from the reference's mode table (src/project.cpp:31-44,67-108) and type switch (:111-132). */
@@ -134,6 +133,15 @@ int sdrb_chain_process_host(sdrb_chain* c, const uint8_t* h_iq, size_t iq_pitch)
 
 int sdrb_chain_sync(sdrb_chain* c);
 
+/* 1 (default): the front end of block b+1 (RF front-end, band filters) may run concurrently with the PLL
+ * and back end of block b on separate CUDA streams (the rings are three slots deep for this).
+ * 0: every kernel of a block is issued on one stream, in order. */
+int sdrb_chain_set_overlap(sdrb_chain* c, int on);
+
+/* Page-locked host memory for process_host / read_* buffers (cudaHostAlloc / cudaFreeHost). */
+int sdrb_pinned_alloc(size_t bytes, void** h_ptr);
+int sdrb_pinned_free(void* h_ptr);
+
 /* Results of the most recent block.
  * pcm: [n_streams][pcm_pitch] int16, what mono()/stereo() fwrite to stdout (src/mono.cpp:40-45,
  *      src/stereo.cpp:100-111): L on even, R on odd indices for stereo. */
@@ -156,7 +164,7 @@ int sdrb_chain_read_rds(sdrb_chain* c, sdrb_rds_record* h_records /* [n_streams]
 int sdrb_rds_parse(uint64_t group, uint64_t* chars, uint64_t* output, char* text, int text_cap);
 
 /* Intermediates of the most recent block (keep_stages = 1 only).  Names: fm_demod pilot carrier stereo_band
- * mono_filt stereo_filt audio_filt rds_band gen_pilot IPLL rds_filt rds_clean.  Copies `count` floats per
+ * stereo_dc mono_filt stereo_filt audio_filt rds_band gen_pilot IPLL rds_band_delay rds_dc rds_filt rds_clean I_ds Q_ds.  Copies `count` floats per
  * stream into h_out [n_streams][count]; *count is set to the per-stream length. */
 int sdrb_chain_stage(sdrb_chain* c, const char* name, float* h_out, int cap_per_stream, int* count);
 

@@ -355,7 +355,10 @@ SDRB_HD PllCoef pll_coef(float freq, float Fs, float ncoScale, float phaseAdjust
     c.phaseAdjust = phaseAdjust;
     return c;
 }
-SDRB_HD float pll_step(float in, PllState& st, const PllCoef& k, const AtanTab& tab) {
+// The recurrence proper (:36-50): consumes one input sample, updates the loop state and returns trigArg.
+// The NCO output of :52 is a pure function of trigArg (nco_out below), so callers that batch many
+// streams keep it out of the sequential loop.
+SDRB_HD float pll_step_trig(float in, PllState& st, const PllCoef& k, const AtanTab& tab) {
     float errorI = fmul(in, st.feedbackI);
     float errorQ = fmul(in, -st.feedbackQ);
     float errorD = atan2_f(errorQ, errorI, tab);
@@ -364,7 +367,11 @@ SDRB_HD float pll_step(float in, PllState& st, const PllCoef& k, const AtanTab& 
     st.trigOffset = dadd(st.trigOffset, 1.0);
     float trigArg = (float)dadd(dmul(k.w, st.trigOffset), (double)st.phaseEst);
     sincos_f(trigArg, st.feedbackQ, st.feedbackI);
-    return cos_f(fadd(fmul(trigArg, k.ncoScale), k.phaseAdjust));
+    return trigArg;
+}
+SDRB_HD float nco_out(float trigArg, const PllCoef& k) { return cos_f(fadd(fmul(trigArg, k.ncoScale), k.phaseAdjust)); }
+SDRB_HD float pll_step(float in, PllState& st, const PllCoef& k, const AtanTab& tab) {
+    return nco_out(pll_step_trig(in, st, k, tab), k);
 }
 
 }  // namespace cr

@@ -1,0 +1,856 @@
+// libsdr_b200: host orchestration and C ABI (include/sdr_b200.h) of the B200 receive chain.
+//
+// One sdrb_chain owns the carried state of n_streams independent stations on one GPU and turns one
+// block of 8-bit IQ per station into PCM audio and an RDS record per call, doing what the reference's
+// three thread bodies do per block (/root/reference/src/rffrontend.cpp:45-76, src/mono.cpp:29-49,
+// src/stereo.cpp:69-114, src/rds.cpp:95-192).  There is no CPU fallback: without a usable GPU every
+// entry point that needs one fails with SDRB_ERR_NO_DEVICE / SDRB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sdr_b200.h"
+#include "sdr_kernels.cuh"
+
+using namespace sdrb;
+
+static_assert(sizeof(RdsRecord) == sizeof(sdrb_rds_record), "RdsRecord must mirror sdrb_rds_record");
+static_assert(sizeof(PllStateAbi) == sizeof(sdrb_pll_state), "PllStateAbi must mirror sdrb_pll_state");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SDRB_ERR_NO_DEVICE : SDRB_ERR_CUDA;
+}
+#define CU(x)                                             \
+    do {                                                  \
+        cudaError_t e_ = (x);                             \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #x);  \
+    } while (0)
+
+inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+struct Ring {
+    float* base = nullptr;
+    size_t pitch = 0, slot = 0;
+    int halo = 0, n = 0;
+    RingView view(long long b) const {
+        RingView v;
+        v.cur = base + (size_t)(b % kNRing) * slot + halo;
+        v.nxt = base + (size_t)((b + 1) % kNRing) * slot + halo;
+        v.pitch = pitch;
+        v.halo = halo;
+        v.n = n;
+        return v;
+    }
+    const float* cur(long long b) const { return base + (size_t)(b % kNRing) * slot + halo; }
+};
+
+struct Timed {
+    const char* name;
+    cudaEvent_t e0, e1;
+    bool used;
+};
+
+}  // namespace
+
+struct sdrb_chain {
+    sdrb_config cfg;
+    sdrb_chain_info info;
+    int S = 0;
+    int up = 1, down = 5;
+    bool stereo = false, rds = false;
+    long long block = 0;  // index of the next block to process
+    long long launches = 0;
+    cudaStream_t stream = nullptr;
+    // taps
+    Taps101 rf_h, pilot_h, stereo_h, rds_h, rds114_h, rrc_h, audio_h;
+    float* d_audio_pm = nullptr;   // phase-major audio taps (up > 1)
+    float* d_rds_perm = nullptr;   // permuted RDS low-pass taps
+    // input
+    uint8_t* d_iq[2] = {nullptr, nullptr};  // staging for process_host
+    size_t iq_pitch = 0;
+    uint8_t* d_iq_halo[2] = {nullptr, nullptr};
+    // rings
+    Ring fm, pilot, sband, rband, gpilot, trig19, trig114, sdc, rdc;
+    // states
+    PllStateDev* d_pll[2] = {nullptr, nullptr};
+    float* d_filt_state[2] = {nullptr, nullptr};
+    RdsStreamState* d_rds_state = nullptr;
+    RdsRecord* d_rec = nullptr;
+    // outputs
+    int16_t* d_pcm = nullptr;
+    size_t pcm_pitch = 0;
+    // optional stage dumps
+    float *d_ids = nullptr, *d_qds = nullptr, *d_carrier = nullptr, *d_ipll = nullptr, *d_rdelay = nullptr,
+          *d_mono = nullptr, *d_sfilt = nullptr, *d_rfilt = nullptr, *d_rclean = nullptr;
+    // profiling
+    bool profiling = false;
+    bool overlap = false;
+    std::vector<Timed> timed;
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+int dalloc(sdrb_chain* c, void** p, size_t bytes, int fill = 0) {
+    CU(cudaMalloc(p, bytes));
+    c->allocs.push_back(*p);
+    CU(cudaMemsetAsync(*p, fill, bytes, c->stream));
+    return SDRB_OK;
+}
+
+int ring_alloc(sdrb_chain* c, Ring& r, int n, int halo) {
+    r.n = n;
+    r.halo = halo;
+    r.pitch = round_up((size_t)halo + n + 4, 4);
+    r.slot = r.pitch * c->S;
+    return dalloc(c, (void**)&r.base, sizeof(float) * r.slot * kNRing);
+}
+
+void copy_taps(Taps101& t, const std::vector<float>& h) { memcpy(t.h, h.data(), sizeof(float) * kTaps); }
+
+Timed* timer_for(sdrb_chain* c, const char* name) {
+    for (auto& t : c->timed)
+        if (strcmp(t.name, name) == 0) return &t;
+    Timed t{name, nullptr, nullptr, false};
+    cudaEventCreate(&t.e0);
+    cudaEventCreate(&t.e1);
+    c->timed.push_back(t);
+    return &c->timed.back();
+}
+
+struct ScopedTimer {
+    sdrb_chain* c;
+    Timed* t = nullptr;
+    ScopedTimer(sdrb_chain* c_, const char* name) : c(c_) {
+        if (c->profiling) {
+            t = timer_for(c, name);
+            t->used = true;
+            cudaEventRecord(t->e0, c->stream);
+        }
+    }
+    ~ScopedTimer() {
+        if (t) cudaEventRecord(t->e1, c->stream);
+    }
+};
+
+int check_launch(sdrb_chain* c, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    c->launches++;
+    return SDRB_OK;
+}
+
+template <int DECIM>
+int launch_rf(sdrb_chain* c, const RfArgs& a) {
+    dim3 grid((c->info.if_block + kRfTile - 2) / (kRfTile - 1), c->S);
+    k_rf_frontend<DECIM><<<grid, kRfThreads, 0, c->stream>>>(c->rf_h, a);
+    return check_launch(c, "k_rf_frontend");
+}
+
+template <int DOWN>
+int launch_audio_decim(sdrb_chain* c, const AudioArgs& a) {
+    dim3 grid((a.n_out + kAudTile - 1) / kAudTile, c->S);
+    if (c->stereo) k_audio_decim<DOWN, true><<<grid, kAudThreads, 0, c->stream>>>(c->audio_h, a);
+    else k_audio_decim<DOWN, false><<<grid, kAudThreads, 0, c->stream>>>(c->audio_h, a);
+    return check_launch(c, "k_audio_decim");
+}
+
+int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch) {
+    const long long b = c->block;
+    const int S = c->S, n_if = c->info.if_block;
+    const bool keep = c->cfg.keep_stages != 0;
+    int rc;
+    {
+        ScopedTimer tm(c, "rf_frontend");
+        RfArgs a{};
+        a.iq = d_iq;
+        a.iq_pitch = iq_pitch;
+        a.halo_in = c->d_iq_halo[b & 1];
+        a.halo_out = c->d_iq_halo[(b + 1) & 1];
+        a.block_pairs = c->info.block_pairs;
+        a.if_block = n_if;
+        a.fm = c->fm.view(b);
+        a.i_ds = keep ? c->d_ids : nullptr;
+        a.q_ds = keep ? c->d_qds : nullptr;
+        switch (c->cfg.rf_decim) {
+            case 10: rc = launch_rf<10>(c, a); break;
+            case 4: rc = launch_rf<4>(c, a); break;
+            case 3: rc = launch_rf<3>(c, a); break;
+            default: return fail(SDRB_ERR_INVALID, "rf_decim must be 10, 4 or 3");
+        }
+        if (rc) return rc;
+    }
+    const int tiles = (n_if + kBankTile - 1) / kBankTile;
+    const int bank_blocks = (int)(((long long)S * tiles + kBankWarps - 1) / kBankWarps);
+    if (c->stereo && c->rds) {
+        ScopedTimer tm(c, "if_bands");
+        BankArgs<3> a{};
+        a.x = c->fm.cur(b); a.x_pitch = c->fm.pitch; a.n = n_if; a.tiles = tiles; a.n_streams = S;
+        a.y[0] = c->pilot.view(b); a.y[1] = c->sband.view(b); a.y[2] = c->rband.view(b);
+        a.taps[0] = c->pilot_h; a.taps[1] = c->stereo_h; a.taps[2] = c->rds_h;
+        k_fir_bank<3, false><<<bank_blocks, 32 * kBankWarps, 0, c->stream>>>(a);
+        if ((rc = check_launch(c, "k_fir_bank<3>"))) return rc;
+    } else if (c->stereo) {
+        ScopedTimer tm(c, "if_bands");
+        BankArgs<2> a{};
+        a.x = c->fm.cur(b); a.x_pitch = c->fm.pitch; a.n = n_if; a.tiles = tiles; a.n_streams = S;
+        a.y[0] = c->pilot.view(b); a.y[1] = c->sband.view(b);
+        a.taps[0] = c->pilot_h; a.taps[1] = c->stereo_h;
+        k_fir_bank<2, false><<<bank_blocks, 32 * kBankWarps, 0, c->stream>>>(a);
+        if ((rc = check_launch(c, "k_fir_bank<2>"))) return rc;
+    }
+    if (c->rds) {
+        ScopedTimer tm(c, "rds_carrier_bpf");
+        BankArgs<1> a{};
+        a.x = c->rband.cur(b); a.x_pitch = c->rband.pitch; a.n = n_if; a.tiles = tiles; a.n_streams = S;
+        a.y[0] = c->gpilot.view(b);
+        a.taps[0] = c->rds114_h;
+        k_fir_bank<1, true><<<bank_blocks, 32 * kBankWarps, 0, c->stream>>>(a);
+        if ((rc = check_launch(c, "k_fir_bank<1,sq>"))) return rc;
+    }
+    if (c->stereo) {
+        ScopedTimer tm(c, "pll");
+        PllArgs a{};
+        a.n = n_if; a.n_streams = S;
+        const float if_fs = (float)(c->cfg.rf_Fs / c->cfg.rf_decim);
+        a.loop[0].x = c->pilot.cur(b); a.loop[0].x_pitch = c->pilot.pitch; a.loop[0].trig = c->trig19.view(b);
+        a.loop[0].st = c->d_pll[0];
+        a.loop[0].coef = cr::pll_coef(19e3f, if_fs, 2.0f, 0.0f, 0.01f);        // src/stereo.cpp:77
+        if (c->rds) {
+            a.loop[1].x = c->gpilot.cur(b); a.loop[1].x_pitch = c->gpilot.pitch; a.loop[1].trig = c->trig114.view(b);
+            a.loop[1].st = c->d_pll[1];
+            a.loop[1].coef = cr::pll_coef(114e3f, (float)c->cfg.if_Fs, 0.5f, 0.0f, 0.001f);  // src/rds.cpp:119
+        }
+        dim3 grid((S + kPllThreads - 1) / kPllThreads, c->rds ? 2 : 1);
+        k_pll<<<grid, kPllThreads, 0, c->stream>>>(a);
+        if ((rc = check_launch(c, "k_pll"))) return rc;
+    }
+    if (c->stereo) {
+        ScopedTimer tm(c, "mix");
+        MixArgs a{};
+        a.n = n_if; a.n_streams = S; a.do_stereo = 1;
+        a.band = c->sband.cur(b); a.band_pitch = c->sband.pitch;
+        a.trig19 = c->trig19.cur(b); a.trig19_pitch = c->trig19.pitch;
+        a.stereo_dc = c->sdc.view(b);
+        a.carrier_out = keep ? c->d_carrier : nullptr;
+        a.scale19 = 2.0f; a.adjust19 = 0.0f; a.scale114 = 0.5f; a.adjust114 = 0.0f;
+        if (c->rds) {
+            a.rds_band = c->rband.cur(b); a.rds_band_pitch = c->rband.pitch;
+            a.trig114 = c->trig114.cur(b); a.trig114_pitch = c->trig114.pitch;
+            a.rds_dc = c->rdc.view(b);
+            a.ipll_out = keep ? c->d_ipll : nullptr;
+            a.delay_out = keep ? c->d_rdelay : nullptr;
+        }
+        dim3 grid((n_if + 1 + 255) / 256, S);
+        k_mix<<<grid, 256, 0, c->stream>>>(a);
+        if ((rc = check_launch(c, "k_mix"))) return rc;
+    }
+    {
+        ScopedTimer tm(c, "audio");
+        AudioArgs a{};
+        // stereo(): mono path = 50-sample all-pass delay of fm_demod (src/stereo.cpp:88); mono(): fm_demod itself
+        a.mono_x = c->fm.cur(b) - (c->stereo ? 50 : 0);
+        a.mono_pitch = c->fm.pitch;
+        a.dc_x = c->stereo ? c->sdc.cur(b) : nullptr;
+        a.dc_pitch = c->sdc.pitch;
+        a.n_in = n_if; a.n_out = c->info.audio_block; a.up = c->up; a.down = c->down;
+        a.taps_pm = c->d_audio_pm;
+        a.pcm = c->d_pcm; a.pcm_pitch = c->pcm_pitch;
+        a.mono_out = keep ? c->d_mono : nullptr;
+        a.dc_out = keep ? c->d_sfilt : nullptr;
+        if (c->up == 1 && c->down == 5) rc = launch_audio_decim<5>(c, a);
+        else if (c->up == 1 && c->down == 9) rc = launch_audio_decim<9>(c, a);
+        else {
+            dim3 grid((a.n_out + 127) / 128, S);
+            if (c->stereo) k_audio_updown<true><<<grid, 128, 0, c->stream>>>(a);
+            else k_audio_updown<false><<<grid, 128, 0, c->stream>>>(a);
+            rc = check_launch(c, "k_audio_updown");
+        }
+        if (rc) return rc;
+    }
+    if (c->rds) {
+        ScopedTimer tm(c, "rds_backend");
+        RdsArgs a{};
+        a.dc = c->rdc.cur(b); a.dc_pitch = c->rdc.pitch;
+        a.n_in = n_if; a.n_out = c->info.rds_block; a.sps = 39; a.rds_on = c->cfg.rds_on;
+        a.taps_perm = c->d_rds_perm;
+        a.rrc = c->rrc_h;
+        a.filt_state_in = c->d_filt_state[b & 1];
+        a.filt_state_out = c->d_filt_state[(b + 1) & 1];
+        a.st = c->d_rds_state;
+        a.rec = c->d_rec;
+        a.filt_out = keep ? c->d_rfilt : nullptr;
+        a.clean_out = keep ? c->d_rclean : nullptr;
+        const int rrc_tiles = (a.n_out + kRrcTile - 1) / kRrcTile;
+        const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;
+        const size_t smem = sizeof(float) * (round_up(n_if + kState, 4) + nfilt + nfilt / kRrcR + 8);
+        k_rds_backend<<<S, kRdsThreads, smem, c->stream>>>(a);
+        if ((rc = check_launch(c, "k_rds_backend"))) return rc;
+    }
+    c->block = b + 1;
+    return SDRB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sdrb_last_error(void) { return g_err.c_str(); }
+int sdrb_version(void) { return 100; }
+
+int sdrb_config_for_mode(int mode, int type, int n_streams, sdrb_config* cfg) {
+    if (!cfg) return fail(SDRB_ERR_INVALID, "cfg is null");
+    if (type != 'm' && type != 's' && type != 'r') return fail(SDRB_ERR_INVALID, "type must be 'm', 's' or 'r'");
+    memset(cfg, 0, sizeof(*cfg));
+    // defaults, /root/reference/src/project.cpp:31-44
+    cfg->rf_Fs = 2400000; cfg->rf_Fc = 100000; cfg->rf_taps = kTaps; cfg->rf_decim = 10;
+    cfg->audio_decim = 5; cfg->audio_upsample = 1; cfg->if_Fs = 240000; cfg->audio_Fc = 16000;
+    cfg->audio_Fs = 48000; cfg->symbol_Fs = 39;
+    switch (mode) {  // :67-108
+        case 0: break;
+        case 1: cfg->rf_Fs = 1440000; cfg->rf_decim = 4; cfg->audio_decim = 9; cfg->if_Fs = 360000; cfg->audio_Fs = 40000; break;
+        case 2: cfg->audio_decim = 800; cfg->audio_upsample = 147; cfg->audio_Fs = 44100; cfg->symbol_Fs = 20; break;
+        case 3: cfg->rf_Fs = 1152000; cfg->rf_decim = 3; cfg->audio_decim = 1280; cfg->audio_upsample = 147;
+                cfg->if_Fs = 384000; cfg->audio_Fs = 44100; cfg->symbol_Fs = 20; break;
+        default: return fail(SDRB_ERR_INVALID, "mode must be 0..3");
+    }
+    cfg->rds_on = (type == 'r');  // :111-132
+    cfg->type = type;
+    cfg->n_streams = n_streams;
+    cfg->device = 0;
+    cfg->keep_stages = 0;
+    return SDRB_OK;
+}
+
+int sdrb_chain_destroy(sdrb_chain* c) {
+    if (!c) return SDRB_OK;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    for (auto& t : c->timed) {
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SDRB_OK;
+}
+
+int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
+    if (!cfg || !out) return fail(SDRB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->n_streams < 1 || cfg->n_streams > 65535) return fail(SDRB_ERR_INVALID, "n_streams must be in 1..65535");
+    if (cfg->rf_taps != kTaps) return fail(SDRB_ERR_INVALID, "rf_taps must be 101");
+    if (cfg->type != 'm' && cfg->type != 's' && cfg->type != 'r') return fail(SDRB_ERR_INVALID, "bad type");
+    if (cfg->rf_decim != 10 && cfg->rf_decim != 4 && cfg->rf_decim != 3) return fail(SDRB_ERR_INVALID, "rf_decim must be 10, 4 or 3");
+    if (cfg->audio_upsample < 1 || cfg->audio_decim < 1) return fail(SDRB_ERR_INVALID, "bad audio resampling ratio");
+    if (cfg->type == 'r' && !(cfg->if_Fs == 240000 && cfg->audio_upsample == 1))
+        return fail(SDRB_ERR_INVALID, "RDS needs if_Fs = 240 kHz (mode 0): the reference hard-codes 247/640 and 39 samples per symbol");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_err = "no CUDA device available (libsdr_b200 has no CPU fallback)";
+        if (e != cudaSuccess) g_err += std::string(": ") + cudaGetErrorString(e);
+        return SDRB_ERR_NO_DEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SDRB_ERR_INVALID, "bad device ordinal");
+    CU(cudaSetDevice(cfg->device));
+
+    sdrb_chain* c = new sdrb_chain();
+    c->cfg = *cfg;
+    c->S = cfg->n_streams;
+    c->up = cfg->audio_upsample;
+    c->down = cfg->audio_decim;
+    c->stereo = cfg->type != 'm';
+    c->rds = cfg->type == 'r';
+    sdrb_chain_info& I = c->info;
+    I.block_pairs = (1470 * cfg->rf_decim * c->down) / c->up;  // src/rffrontend.cpp:21
+    I.block_bytes = 2 * I.block_pairs;
+    I.if_block = (1470 * c->down) / c->up;                     // src/mono.cpp:19
+    I.audio_block = (int)(((long long)I.if_block * c->up) / c->down);
+    I.pcm_per_block = I.audio_block * (c->stereo ? 2 : 1);
+    I.rds_block = (int)(((long long)I.if_block * kRdsUp) / kRdsDown);
+    I.max_bits = kRdsMaxBits;
+    I.max_groups = kRdsMaxGroups;
+    const int S = c->S, n_if = I.if_block;
+
+#define TRY(x)                        \
+    do {                              \
+        int rc_ = (x);                \
+        if (rc_) {                    \
+            sdrb_chain_destroy(c);    \
+            return rc_;               \
+        }                             \
+    } while (0)
+#define TRYCU(x)                                   \
+    do {                                           \
+        cudaError_t e_ = (x);                      \
+        if (e_ != cudaSuccess) {                   \
+            int rc_ = cuda_fail(e_, #x);           \
+            sdrb_chain_destroy(c);                 \
+            return rc_;                            \
+        }                                          \
+    } while (0)
+
+    TRYCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+    // ---- taps (all designed on the host, same libm as the reference build)
+    std::vector<float> h(kTaps);
+    const float if_fs_f = (float)(cfg->rf_Fs / cfg->rf_decim);
+    sdrb_design_lpf((float)cfg->rf_Fs, (float)cfg->rf_Fc, kTaps, h.data());            // src/rffrontend.cpp:24
+    copy_taps(c->rf_h, h);
+    sdrb_design_bpf(if_fs_f, 18.5e3f, 19.5e3f, kTaps, h.data());                       // src/stereo.cpp:65
+    copy_taps(c->pilot_h, h);
+    sdrb_design_bpf(if_fs_f, 22e3f, 54e3f, kTaps, h.data());                           // src/stereo.cpp:67
+    copy_taps(c->stereo_h, h);
+    sdrb_design_bpf((float)cfg->if_Fs, 54e3f, 60e3f, kTaps, h.data());                 // src/rds.cpp:62
+    copy_taps(c->rds_h, h);
+    sdrb_design_bpf((float)cfg->if_Fs, 113.5e3f, 114.5e3f, kTaps, h.data());           // src/rds.cpp:63
+    copy_taps(c->rds114_h, h);
+    sdrb_design_rrc((float)(2375 * 39), kTaps, h.data());                              // src/rds.cpp:65 (sps = 39)
+    copy_taps(c->rrc_h, h);
+    {
+        const int nh = kTaps * c->up;
+        std::vector<float> ah(nh);
+        sdrb_design_lpf_gain((float)cfg->if_Fs * (float)c->up, (float)cfg->audio_Fc, nh, c->up, ah.data());  // src/mono.cpp:22
+        if (c->up == 1) {
+            copy_taps(c->audio_h, ah);
+        } else {
+            std::vector<float> pm((size_t)c->up * kTaps);
+            for (int p = 0; p < c->up; p++)
+                for (int j = 0; j < kTaps; j++) pm[(size_t)p * kTaps + j] = ah[p + c->up * j];
+            TRY(dalloc(c, (void**)&c->d_audio_pm, pm.size() * sizeof(float)));
+            TRYCU(cudaMemcpyAsync(c->d_audio_pm, pm.data(), pm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            TRYCU(cudaStreamSynchronize(c->stream));
+        }
+    }
+    if (c->rds) {
+        const int nh = kTaps * kRdsUp;
+        std::vector<float> lh(nh);
+        sdrb_design_lpf_gain((float)(cfg->if_Fs * kRdsUp), 3e3f, nh, kRdsUp, lh.data());  // src/rds.cpp:61
+        std::vector<float> perm((size_t)kTaps * 256, 0.0f);
+        for (int t = 0; t < kRdsUp; t++) {
+            const int phase = (kRdsDown * t) % kRdsUp;
+            for (int j = 0; j < kTaps; j++) perm[(size_t)j * 256 + t] = lh[phase + kRdsUp * j];
+        }
+        TRY(dalloc(c, (void**)&c->d_rds_perm, perm.size() * sizeof(float)));
+        TRYCU(cudaMemcpyAsync(c->d_rds_perm, perm.data(), perm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        TRYCU(cudaStreamSynchronize(c->stream));
+    }
+
+    // ---- input staging and halo (bytes; 128 unpacks to 0.0f = the reference's zero-initialised state)
+    c->iq_pitch = round_up((size_t)I.block_bytes, 256);
+    for (int i = 0; i < 2; i++) {
+        TRY(dalloc(c, (void**)&c->d_iq[i], c->iq_pitch * S));
+        TRY(dalloc(c, (void**)&c->d_iq_halo[i], (size_t)2 * kIqHaloPairs * S, 128));
+    }
+    // ---- rings
+    TRY(ring_alloc(c, c->fm, n_if, 160));
+    if (c->stereo) {
+        TRY(ring_alloc(c, c->pilot, n_if, 0));
+        TRY(ring_alloc(c, c->sband, n_if, 0));
+        TRY(ring_alloc(c, c->trig19, n_if, 4));
+        TRY(ring_alloc(c, c->sdc, n_if, 112));
+        TRY(dalloc(c, (void**)&c->d_pll[0], sizeof(PllStateDev) * S));
+    }
+    if (c->rds) {
+        TRY(ring_alloc(c, c->rband, n_if, 160));
+        TRY(ring_alloc(c, c->gpilot, n_if, 0));
+        TRY(ring_alloc(c, c->trig114, n_if, 4));
+        TRY(ring_alloc(c, c->rdc, n_if, 112));
+        TRY(dalloc(c, (void**)&c->d_pll[1], sizeof(PllStateDev) * S));
+        for (int i = 0; i < 2; i++) TRY(dalloc(c, (void**)&c->d_filt_state[i], sizeof(float) * kState * S));
+        TRY(dalloc(c, (void**)&c->d_rds_state, sizeof(RdsStreamState) * S));
+        TRY(dalloc(c, (void**)&c->d_rec, sizeof(RdsRecord) * S));
+    }
+    {   // PLL initial state: feedbackI = 1, rest 0 (src/stereo.cpp:51-57, src/rds.cpp:51-56)
+        std::vector<PllStateDev> init(S, PllStateDev{1.0f, 0.0f, 0.0f, 0.0f, 0.0});
+        for (int i = 0; i < 2; i++)
+            if (c->d_pll[i]) TRYCU(cudaMemcpyAsync(c->d_pll[i], init.data(), sizeof(PllStateDev) * S, cudaMemcpyHostToDevice, c->stream));
+        if (c->d_rds_state) {
+            std::vector<RdsStreamState> rs(S);
+            memset(rs.data(), 0, sizeof(RdsStreamState) * S);
+            for (auto& r : rs) r.first_time = 1;
+            TRYCU(cudaMemcpyAsync(c->d_rds_state, rs.data(), sizeof(RdsStreamState) * S, cudaMemcpyHostToDevice, c->stream));
+        }
+        TRYCU(cudaStreamSynchronize(c->stream));
+    }
+    c->pcm_pitch = round_up((size_t)I.pcm_per_block, 8);
+    TRY(dalloc(c, (void**)&c->d_pcm, sizeof(int16_t) * c->pcm_pitch * S));
+    if (cfg->keep_stages) {
+        TRY(dalloc(c, (void**)&c->d_ids, sizeof(float) * n_if * S));
+        TRY(dalloc(c, (void**)&c->d_qds, sizeof(float) * n_if * S));
+        TRY(dalloc(c, (void**)&c->d_mono, sizeof(float) * I.audio_block * S));
+        if (c->stereo) {
+            TRY(dalloc(c, (void**)&c->d_carrier, sizeof(float) * (n_if + 1) * S));
+            TRY(dalloc(c, (void**)&c->d_sfilt, sizeof(float) * I.audio_block * S));
+        }
+        if (c->rds) {
+            TRY(dalloc(c, (void**)&c->d_ipll, sizeof(float) * (n_if + 1) * S));
+            TRY(dalloc(c, (void**)&c->d_rdelay, sizeof(float) * n_if * S));
+            TRY(dalloc(c, (void**)&c->d_rfilt, sizeof(float) * I.rds_block * S));
+            TRY(dalloc(c, (void**)&c->d_rclean, sizeof(float) * I.rds_block * S));
+        }
+    }
+    if (c->rds) {
+        const int rrc_tiles = (I.rds_block + kRrcTile - 1) / kRrcTile;
+        const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;
+        const size_t smem = sizeof(float) * (round_up(n_if + kState, 4) + nfilt + nfilt / kRrcR + 8);
+        TRYCU(cudaFuncSetAttribute(k_rds_backend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    TRYCU(cudaStreamSynchronize(c->stream));
+#undef TRY
+#undef TRYCU
+    *out = c;
+    return SDRB_OK;
+}
+
+int sdrb_chain_get_info(const sdrb_chain* c, sdrb_chain_info* info) {
+    if (!c || !info) return fail(SDRB_ERR_INVALID, "null argument");
+    *info = c->info;
+    return SDRB_OK;
+}
+
+int sdrb_chain_process_device(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch) {
+    if (!c || !d_iq) return fail(SDRB_ERR_INVALID, "null argument");
+    if (iq_pitch < (size_t)c->info.block_bytes || (iq_pitch & 1)) return fail(SDRB_ERR_INVALID, "iq_pitch too small or odd");
+    if ((reinterpret_cast<uintptr_t>(d_iq) & 1)) return fail(SDRB_ERR_INVALID, "d_iq must be 2-byte aligned");
+    CU(cudaSetDevice(c->cfg.device));
+    return process_block(c, d_iq, iq_pitch);
+}
+
+int sdrb_chain_process_host(sdrb_chain* c, const uint8_t* h_iq, size_t iq_pitch) {
+    if (!c || !h_iq) return fail(SDRB_ERR_INVALID, "null argument");
+    if (iq_pitch < (size_t)c->info.block_bytes) return fail(SDRB_ERR_INVALID, "iq_pitch too small");
+    CU(cudaSetDevice(c->cfg.device));
+    uint8_t* dst = c->d_iq[c->block & 1];
+    CU(cudaMemcpy2DAsync(dst, c->iq_pitch, h_iq, iq_pitch, c->info.block_bytes, c->S, cudaMemcpyHostToDevice, c->stream));
+    return process_block(c, dst, c->iq_pitch);
+}
+
+int sdrb_chain_sync(sdrb_chain* c) {
+    if (!c) return fail(SDRB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    return SDRB_OK;
+}
+
+int sdrb_chain_set_overlap(sdrb_chain* c, int on) {
+    if (!c) return fail(SDRB_ERR_INVALID, "null argument");
+    c->overlap = on != 0;
+    return SDRB_OK;
+}
+
+int sdrb_pinned_alloc(size_t bytes, void** h_ptr) {
+    if (!h_ptr || bytes == 0) return fail(SDRB_ERR_INVALID, "bad argument");
+    CU(cudaHostAlloc(h_ptr, bytes, cudaHostAllocDefault));
+    return SDRB_OK;
+}
+
+int sdrb_pinned_free(void* h_ptr) {
+    if (h_ptr) CU(cudaFreeHost(h_ptr));
+    return SDRB_OK;
+}
+
+int sdrb_chain_read_pcm(sdrb_chain* c, int16_t* h_pcm, size_t pcm_pitch) {
+    if (!c || !h_pcm) return fail(SDRB_ERR_INVALID, "null argument");
+    if (c->block == 0) return fail(SDRB_ERR_STATE, "no block processed yet");
+    if (pcm_pitch < (size_t)c->info.pcm_per_block) return fail(SDRB_ERR_INVALID, "pcm_pitch too small");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMemcpy2DAsync(h_pcm, pcm_pitch * sizeof(int16_t), c->d_pcm, c->pcm_pitch * sizeof(int16_t),
+                         c->info.pcm_per_block * sizeof(int16_t), c->S, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SDRB_OK;
+}
+
+int sdrb_chain_pcm_device(sdrb_chain* c, const int16_t** d_pcm, size_t* pcm_pitch) {
+    if (!c || !d_pcm || !pcm_pitch) return fail(SDRB_ERR_INVALID, "null argument");
+    *d_pcm = c->d_pcm;
+    *pcm_pitch = c->pcm_pitch;
+    return SDRB_OK;
+}
+
+int sdrb_chain_read_rds(sdrb_chain* c, sdrb_rds_record* h_records) {
+    if (!c || !h_records) return fail(SDRB_ERR_INVALID, "null argument");
+    if (!c->rds) return fail(SDRB_ERR_STATE, "chain was created without RDS (type != 'r')");
+    if (c->block == 0) return fail(SDRB_ERR_STATE, "no block processed yet");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMemcpyAsync(h_records, c->d_rec, sizeof(RdsRecord) * c->S, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SDRB_OK;
+}
+
+// parse(), /root/reference/src/rds_utilities.cpp:172-199 (+ stringify :111-119): "PI: " in lower-case hex
+// without padding (std::hex), "PTY: " by name, on every group; type-0 groups fill the 8-character PS
+// buffer and print it when segment 3 arrives and the buffer changed (printed as a C string).
+int sdrb_rds_parse(uint64_t group, uint64_t* chars, uint64_t* output, char* text, int text_cap) {
+    static const char* const pty_names[32] = {  // :137-170
+        "Undefined", "News", "Information", "Sports", "Talk", "Rock", "Classic Rock", "Adult Hits", "Soft Rock",
+        "Top 40", "Country", "Oldies", "Soft", "Nostalgia", "Jazz", "Classical", "Rhythm & Blues",
+        "Soft Rhythm & Blues", "Language", "Religious Music", "Religious Talk", "Personality", "Public", "College",
+        "Spanish Talk", "Spanish Music", "Hip Hop", "Unassigned", "Unassigned", "Weather", "Emergency Test",
+        "Emergency"};
+    if (!chars || !output || !text || text_cap < 1) return 0;
+    const unsigned group_type = (unsigned)(group >> 44) & 0xF;
+    const unsigned segment = (unsigned)(group >> 32) & 0x3;
+    const unsigned pi = (unsigned)(group >> 48) & 0xFFFF;
+    const unsigned pty = (unsigned)(group >> 37) & 0x1F;
+    std::string out;
+    char line[96];
+    snprintf(line, sizeof line, "PI: %x\nPTY: %s\n", pi, pty_names[pty]);
+    out += line;
+    if (group_type == 0) {
+        const int sh = 16 * (3 - (int)segment);
+        *chars = (*chars & ~((uint64_t)0xFFFF << sh)) | ((group & 0xFFFFull) << sh);
+        if (segment == 3 && *chars != *output) {
+            *output = *chars;
+            char ps[9];
+            for (int i = 0; i < 8; i++) ps[i] = (char)((*chars >> (8 * (7 - i))) & 0xFF);
+            ps[8] = 0;
+            out += "Program Service: ";
+            out += ps;  // C-string semantics: stops at the first NUL
+            out += "\n";
+        }
+    }
+    int n = (int)out.size() < text_cap - 1 ? (int)out.size() : text_cap - 1;
+    memcpy(text, out.data(), n);
+    text[n] = 0;
+    return n;
+}
+
+int sdrb_chain_stage(sdrb_chain* c, const char* name, float* h_out, int cap_per_stream, int* count) {
+    if (!c || !name || !h_out || !count) return fail(SDRB_ERR_INVALID, "null argument");
+    if (!c->cfg.keep_stages) return fail(SDRB_ERR_STATE, "chain was created with keep_stages = 0");
+    if (c->block == 0) return fail(SDRB_ERR_STATE, "no block processed yet");
+    const long long b = c->block - 1;
+    const int n_if = c->info.if_block;
+    const float* src = nullptr;
+    size_t pitch = 0;
+    int n = 0;
+    std::string s(name);
+    auto ring = [&](const Ring& r) { src = r.base ? r.cur(b) : nullptr; pitch = r.pitch; n = r.n; };
+    auto flat = [&](const float* p, int cnt) { src = p; pitch = cnt; n = cnt; };
+    if (s == "fm_demod") ring(c->fm);
+    else if (s == "pilot") ring(c->pilot);
+    else if (s == "stereo_band") ring(c->sband);
+    else if (s == "stereo_dc") ring(c->sdc);
+    else if (s == "rds_band") ring(c->rband);
+    else if (s == "gen_pilot") ring(c->gpilot);
+    else if (s == "rds_dc") ring(c->rdc);
+    else if (s == "I_ds") flat(c->d_ids, n_if);
+    else if (s == "Q_ds") flat(c->d_qds, n_if);
+    else if (s == "carrier") flat(c->d_carrier, n_if + 1);
+    else if (s == "IPLL") flat(c->d_ipll, n_if + 1);
+    else if (s == "rds_band_delay") flat(c->d_rdelay, n_if);
+    else if (s == "mono_filt" || s == "audio_filt") flat(c->d_mono, c->info.audio_block);
+    else if (s == "stereo_filt") flat(c->d_sfilt, c->info.audio_block);
+    else if (s == "rds_filt") flat(c->d_rfilt, c->info.rds_block);
+    else if (s == "rds_clean") flat(c->d_rclean, c->info.rds_block);
+    else return fail(SDRB_ERR_INVALID, "unknown stage name: " + s);
+    if (!src) return fail(SDRB_ERR_STATE, "stage not produced in this configuration: " + s);
+    *count = n;
+    if (cap_per_stream < n) return fail(SDRB_ERR_INVALID, "cap_per_stream too small");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMemcpy2DAsync(h_out, (size_t)cap_per_stream * sizeof(float), src, pitch * sizeof(float), (size_t)n * sizeof(float),
+                         c->S, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SDRB_OK;
+}
+
+// ---- carried state (checkpoint / resume) ---------------------------------------------------------
+// Blob = header {magic, n_streams, if_block, type, block} followed by, per item, the raw device arrays
+// that carry information from one block to the next: the IQ halo, the halo of every ring (as seen by the
+// next block), both PLL states, the RDS resampler state, the per-stream decoder state.
+namespace {
+struct StateItem {
+    void* ptr;        // start (device)
+    size_t row_bytes; // bytes per stream row to save
+    size_t pitch_bytes;
+    int rows;
+};
+std::vector<StateItem> state_items(sdrb_chain* c, long long b /* block that will be processed next */) {
+    std::vector<StateItem> v;
+    const int S = c->S;
+    v.push_back({c->d_iq_halo[b & 1], (size_t)2 * kIqHaloPairs, (size_t)2 * kIqHaloPairs, S});
+    for (Ring* r : {&c->fm, &c->pilot, &c->sband, &c->rband, &c->gpilot, &c->trig19, &c->trig114, &c->sdc, &c->rdc})
+        if (r->base && r->halo > 0)
+            v.push_back({r->base + (size_t)(b % kNRing) * r->slot, (size_t)r->halo * sizeof(float), r->pitch * sizeof(float), S});
+    for (int i = 0; i < 2; i++)
+        if (c->d_pll[i]) v.push_back({c->d_pll[i], sizeof(PllStateDev) * S, sizeof(PllStateDev) * S, 1});
+    if (c->d_filt_state[0]) v.push_back({c->d_filt_state[b & 1], sizeof(float) * kState * S, sizeof(float) * kState * S, 1});
+    if (c->d_rds_state) v.push_back({c->d_rds_state, sizeof(RdsStreamState) * S, sizeof(RdsStreamState) * S, 1});
+    return v;
+}
+struct StateHeader {
+    uint32_t magic, n_streams, if_block, type;
+    long long block;
+};
+constexpr uint32_t kStateMagic = 0x53445242u;
+}  // namespace
+
+size_t sdrb_chain_state_bytes(const sdrb_chain* c) {
+    if (!c) return 0;
+    size_t total = sizeof(StateHeader);
+    for (auto& it : state_items(const_cast<sdrb_chain*>(c), c->block)) total += it.row_bytes * it.rows;
+    return total;
+}
+
+int sdrb_chain_state_save(sdrb_chain* c, void* h_blob) {
+    if (!c || !h_blob) return fail(SDRB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    StateHeader hd{kStateMagic, (uint32_t)c->S, (uint32_t)c->info.if_block, (uint32_t)c->cfg.type, c->block};
+    char* p = static_cast<char*>(h_blob);
+    memcpy(p, &hd, sizeof hd);
+    p += sizeof hd;
+    for (auto& it : state_items(c, c->block)) {
+        CU(cudaMemcpy2D(p, it.row_bytes, it.ptr, it.pitch_bytes, it.row_bytes, it.rows, cudaMemcpyDeviceToHost));
+        p += it.row_bytes * it.rows;
+    }
+    return SDRB_OK;
+}
+
+int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob) {
+    if (!c || !h_blob) return fail(SDRB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    StateHeader hd;
+    const char* p = static_cast<const char*>(h_blob);
+    memcpy(&hd, p, sizeof hd);
+    p += sizeof hd;
+    if (hd.magic != kStateMagic || hd.n_streams != (uint32_t)c->S || hd.if_block != (uint32_t)c->info.if_block ||
+        hd.type != (uint32_t)c->cfg.type)
+        return fail(SDRB_ERR_INVALID, "state blob does not match this chain");
+    c->block = hd.block;
+    for (auto& it : state_items(c, c->block)) {
+        CU(cudaMemcpy2D(it.ptr, it.pitch_bytes, p, it.row_bytes, it.row_bytes, it.rows, cudaMemcpyHostToDevice));
+        p += it.row_bytes * it.rows;
+    }
+    return SDRB_OK;
+}
+
+int sdrb_chain_set_profiling(sdrb_chain* c, int on) {
+    if (!c) return fail(SDRB_ERR_INVALID, "null argument");
+    c->profiling = on != 0;
+    return SDRB_OK;
+}
+
+int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int cap, int* n) {
+    if (!c || !names || !ms || !n) return fail(SDRB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    int k = 0;
+    for (auto& t : c->timed) {
+        if (!t.used || k >= cap) continue;
+        float v = 0;
+        CU(cudaEventElapsedTime(&v, t.e0, t.e1));
+        names[k] = t.name;
+        ms[k] = v;
+        k++;
+    }
+    *n = k;
+    return SDRB_OK;
+}
+
+long long sdrb_chain_launch_count(const sdrb_chain* c) { return c ? c->launches : 0; }
+
+// ---- stand-alone batched primitives ---------------------------------------------------------------
+namespace {
+int upload_taps(const float* h_taps, int nh, float** d, cudaStream_t st) {
+    CU(cudaMallocAsync((void**)d, sizeof(float) * nh, st));
+    CU(cudaMemcpyAsync(*d, h_taps, sizeof(float) * nh, cudaMemcpyHostToDevice, st));
+    return SDRB_OK;
+}
+}  // namespace
+
+int sdrb_fir_decim(const float* d_x, size_t x_pitch, int nx, const float* h_taps, int nh, float* d_state, float* d_y,
+                   size_t y_pitch, int decim, int n_streams, void* stream) {
+    if (!d_x || !h_taps || !d_state || !d_y || nx < 0 || nh < 1 || decim < 1 || n_streams < 1)
+        return fail(SDRB_ERR_INVALID, "bad argument");
+    const int nstate = nh - 1;
+    if (nx < nstate) return fail(SDRB_ERR_INVALID, "nx must be >= nh-1 (the reference reads out of bounds otherwise)");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d_h = nullptr;
+    int rc = upload_taps(h_taps, nh, &d_h, st);
+    if (rc) return rc;
+    const int ny = nx / decim;
+    if (ny > 0) {
+        dim3 grid((ny + 127) / 128, n_streams);
+        k_fir_decim_generic<<<grid, 128, 0, st>>>(d_x, x_pitch, nx, d_h, nh, d_state, nstate, d_y, y_pitch, decim);
+    }
+    if (nstate > 0) {
+        dim3 grid((nstate + 127) / 128, n_streams);
+        k_state_update<<<grid, 128, 0, st>>>(d_x, x_pitch, nx, d_state, nstate);
+    }
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(d_h, st));
+    return SDRB_OK;
+}
+
+int sdrb_fir_updown(const float* d_x, size_t x_pitch, int nx, const float* h_taps, int nh, float* d_state, int nstate,
+                    float* d_y, size_t y_pitch, int up, int down, int n_streams, void* stream) {
+    if (!d_x || !h_taps || !d_state || !d_y || nx < 0 || nh < 1 || up < 1 || down < 1 || n_streams < 1 || nstate < 0)
+        return fail(SDRB_ERR_INVALID, "bad argument");
+    if (nx < nstate) return fail(SDRB_ERR_INVALID, "nx must be >= nstate");
+    if (nstate < (nh - 1) / up) return fail(SDRB_ERR_INVALID, "nstate must be >= (nh-1)/up");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d_h = nullptr;
+    int rc = upload_taps(h_taps, nh, &d_h, st);
+    if (rc) return rc;
+    const int ny = (int)(((long long)nx * up) / down);
+    if (ny > 0) {
+        dim3 grid((ny + 127) / 128, n_streams);
+        k_fir_updown_generic<<<grid, 128, 0, st>>>(d_x, x_pitch, nx, d_h, nh, d_state, nstate, d_y, y_pitch, up, down);
+    }
+    if (nstate > 0) {
+        dim3 grid((nstate + 127) / 128, n_streams);
+        k_state_update<<<grid, 128, 0, st>>>(d_x, x_pitch, nx, d_state, nstate);
+    }
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(d_h, st));
+    return SDRB_OK;
+}
+
+int sdrb_fm_demod(const float* d_I, const float* d_Q, size_t iq_pitch, int n, float* d_prev, float* d_out, size_t out_pitch,
+                  int n_streams, void* stream) {
+    if (!d_I || !d_Q || !d_prev || !d_out || n < 1 || n_streams < 1) return fail(SDRB_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((n + 127) / 128, n_streams);
+    k_fm_demod_generic<<<grid, 128, 0, st>>>(d_I, d_Q, iq_pitch, n, d_prev, d_out, out_pitch);
+    k_fm_prev_update<<<(n_streams + 127) / 128, 128, 0, st>>>(d_I, d_Q, iq_pitch, n, d_prev, n_streams);
+    CU(cudaGetLastError());
+    return SDRB_OK;
+}
+
+int sdrb_pll(const float* d_in, size_t in_pitch, int n, float freq, float Fs, float ncoScale, float phaseAdjust,
+             float normBandwidth, sdrb_pll_state* d_state, float* d_out, size_t out_pitch, int n_streams, void* stream) {
+    if (!d_in || !d_state || !d_out || n < 0 || n_streams < 1) return fail(SDRB_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cr::PllCoef k = cr::pll_coef(freq, Fs, ncoScale, phaseAdjust, normBandwidth);
+    k_pll_generic<<<(n_streams + kPllThreads - 1) / kPllThreads, kPllThreads, 0, st>>>(
+        d_in, in_pitch, n, k, reinterpret_cast<PllStateAbi*>(d_state), d_out, out_pitch, n_streams);
+    CU(cudaGetLastError());
+    return SDRB_OK;
+}
+
+int sdrb_cdr(const float* d_x, size_t x_pitch, int n, int sps, int* d_offset, int n_streams, void* stream) {
+    if (!d_x || !d_offset || n < 0 || sps < 1 || n_streams < 1) return fail(SDRB_ERR_INVALID, "bad argument");
+    k_cdr_generic<<<n_streams, 64, 0, (cudaStream_t)stream>>>(d_x, x_pitch, n, sps, d_offset);
+    CU(cudaGetLastError());
+    return SDRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,907 @@
+// Device kernels of the B200 receive chain (sm_100a).  Host orchestration and the C ABI live in
+// sdr_chain.cu; the correctly-rounded PLL math is pllmath.cuh.
+//
+// Arithmetic contract: every FIR accumulates  acc = RN(acc + RN(h[k]*x[n-k]))  for
+// k = 0..K-1 in that order, starting from +0, exactly like the reference's scalar loops
+// (/root/reference/src/filter.cpp:106-147, compiled without FMA).  All float arithmetic that feeds a
+// result goes through __fmul_rn/__fadd_rn (never contracted) and the file is compiled with -fmad=false.
+//
+// Data layout: every intermediate is a "ring" of NRING slots, each [n_streams][pitch] floats, where a
+// stream row is  [halo | block]  : index -halo..-1 holds the tail of the previous block (what the
+// reference keeps in its `state` vectors), 0..n-1 the current block.  A producer writes block b into
+// slot b%NRING and the tail of that block into the halo of slot (b+1)%NRING, so a consumer always
+// reads one contiguous row and block b+1 can be produced while block b is still being consumed.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pllmath.cuh"
+
+namespace sdrb {
+
+constexpr int kTaps = 101;     // rf_taps, /root/reference/src/project.cpp:34
+constexpr int kState = 100;    // kTaps-1 samples of carried FIR state
+constexpr int kNRing = 3;
+
+struct Taps101 {
+    float h[kTaps];
+};
+
+// One ring (see the layout note above).  `cur` points at sample 0 of stream 0 in the slot being
+// produced/consumed; `nxt` at sample 0 of the following slot (its halo receives the tail).
+struct RingView {
+    float* cur;
+    float* nxt;
+    size_t pitch;  // floats per stream row (halo included)
+    int halo;
+    int n;         // samples per block
+};
+
+__device__ __forceinline__ void ring_store(const RingView& r, int s, int i, float v) {
+    r.cur[(size_t)s * r.pitch + i] = v;
+    int back = r.n - i;  // 1..halo for the tail
+    if (back <= r.halo) r.nxt[(size_t)s * r.pitch - back] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FIR cores.  A thread owns R consecutive outputs and slides a register window over the input, so a
+// tap step costs one shared-memory load per input phase instead of one per MAC.
+//
+// Shared-memory layout: logical sample u (u = 0 is the oldest sample the tile needs) lives at
+// P(u) = u + u / L with L = D*R (the lane stride), which makes the lane stride L+1 (odd) words and all
+// window loads bank-conflict free.  With u = L*lane + c (c a compile-time constant) this is
+// (L+1)*lane + c + c/L, i.e. an immediate offset from a per-lane base.
+// ------------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ int pad_pos(int u) {
+    return u + u / L;
+}
+
+__device__ __forceinline__ float mac(float acc, float h, float x) { return __fadd_rn(acc, __fmul_rn(h, x)); }
+__device__ __forceinline__ float2 mac(float2 acc, float h, float2 x) {
+    return make_float2(__fadd_rn(acc.x, __fmul_rn(h, x.x)), __fadd_rn(acc.y, __fmul_rn(h, x.y)));
+}
+
+// y[m] = sum_k h[k] * x[D*m - k]   for the R outputs m = R*lane + j of this lane.
+// sx_lane = tile base + (L+1)*lane; logical sample index of x[D*m - k] inside the tile is
+// u = D*(R*lane + j) - k + kState.
+template <int D, int R, typename V>
+__device__ __forceinline__ void fir_core(const V* __restrict__ sx_lane, const Taps101& t, V (&acc)[R]) {
+    constexpr int L = D * R;
+    constexpr int A = (kTaps + D - 1) / D;
+    V w[D][R];
+#pragma unroll
+    for (int j = 0; j < R; j++)
+#pragma unroll
+        for (int b = 0; b < D; b++) {
+            const int c = D * j - b + kState;
+            w[b][j] = sx_lane[c + c / L];
+        }
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+        if (a > 0) {
+            const int slot = ((-a) % R + R) % R;
+#pragma unroll
+            for (int b = 0; b < D; b++) {
+                if (D * a + b < kTaps) {
+                    const int c = -D * a - b + kState;
+                    w[b][slot] = sx_lane[c + c / L];
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < D; b++) {
+            const int k = D * a + b;
+            if (k < kTaps) {
+                const float hk = t.h[k];
+#pragma unroll
+                for (int j = 0; j < R; j++) acc[j] = mac(acc[j], hk, w[b][((j - a) % R + R) % R]);
+            }
+        }
+    }
+}
+
+// NF filters over the same input, D = 1.
+template <int NF, int R>
+__device__ __forceinline__ void fir_bank_core(const float* __restrict__ sx_lane, const Taps101* t, float (&acc)[NF][R]) {
+    constexpr int L = R;
+    float w[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int c = j + kState;
+        w[j] = sx_lane[c + c / L];
+    }
+#pragma unroll
+    for (int k = 0; k < kTaps; k++) {
+        if (k > 0) {
+            const int c = -k + kState;
+            w[((-k) % R + R) % R] = sx_lane[c + c / L];
+        }
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            const float hk = t[f].h[k];
+#pragma unroll
+            for (int j = 0; j < R; j++) acc[f][j] = mac(acc[f][j], hk, w[((j - k) % R + R) % R]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  RF front-end: u8 IQ -> unpack -> 101-tap LPF / DECIM on I and Q -> FM discriminator.
+// /root/reference/src/rffrontend.cpp:58-71, src/filter.cpp:106-121, src/demod.cpp:3-24.
+//
+// One CTA = one stream x one tile.  The tile computes kRfTile FIR outputs; the first one only serves
+// as the discriminator's "previous" sample, so tiles advance by kRfTile-1 demodulated samples and the
+// reference's carried prev_I/prev_Q never has to be stored: it is recomputed from the carried input
+// halo (110 IQ pairs, kept as raw bytes; 128 = the byte that unpacks to 0.0f, the initial state).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRfR = 4;
+constexpr int kRfThreads = 64;
+constexpr int kRfTile = kRfR * kRfThreads;  // 256 FIR outputs, 255 discriminator outputs
+constexpr int kIqHaloPairs = 112;           // >= kState + max DECIM; 224 bytes, keeps 16-byte alignment
+
+struct RfArgs {
+    const uint8_t* iq;       // [n_streams][iq_pitch] bytes of the current block
+    size_t iq_pitch;
+    const uint8_t* halo_in;  // [n_streams][2*kIqHaloPairs] last pairs of the previous block
+    uint8_t* halo_out;       // same, for the next block (ping-pong)
+    int block_pairs;
+    int if_block;            // block_pairs / DECIM
+    RingView fm;             // fm_demod
+    float* i_ds;             // optional [n_streams][if_block] (parity tests)
+    float* q_ds;
+};
+
+// (u8 - 128)/128 exactly: 0x4B000000|u is the float 2^23 + u; *2^-7 - 65537 is exact in one FMA.
+__device__ __forceinline__ float unpack_u8(uint32_t u) {
+    return __fmaf_rn(__uint_as_float(0x4B000000u | u), 0.0078125f, -65537.0f);
+}
+
+// (float)(num / (double)I^2 + (double)Q^2), /root/reference/src/demod.cpp:9-18
+__device__ __forceinline__ float fm_discriminate(float I, float Q, float pI, float pQ) {
+    if (I == 0.0f && Q == 0.0f) return 0.0f;
+    float num = __fadd_rn(__fmul_rn(I, __fadd_rn(Q, -pQ)), -__fmul_rn(Q, __fadd_rn(I, -pI)));
+    double den = __dadd_rn(__dmul_rn((double)I, (double)I), __dmul_rn((double)Q, (double)Q));
+    return __double2float_rn(__ddiv_rn((double)num, den));
+}
+
+template <int DECIM>
+__global__ void __launch_bounds__(kRfThreads) k_rf_frontend(const __grid_constant__ Taps101 taps, const RfArgs a) {
+    constexpr int L = DECIM * kRfR;
+    constexpr int NS = DECIM * (kRfTile - 1) + kTaps;  // input pairs a tile needs
+    __shared__ float2 sx[NS + NS / L + 2];
+    __shared__ float2 sy[kRfTile];
+    const int s = blockIdx.y;
+    const int tile = blockIdx.x;
+    const int m0 = tile * (kRfTile - 1) - 1;  // first FIR output of the tile (may be -1)
+    const int g0 = DECIM * m0 - kState;       // first input pair (negative: halo)
+    const uint8_t* blk = a.iq + (size_t)s * a.iq_pitch;
+    const uint8_t* hal = a.halo_in + (size_t)s * (2 * kIqHaloPairs);
+    for (int u = threadIdx.x; u < NS; u += kRfThreads) {
+        int g = g0 + u;
+        uint32_t pr;
+        if (g < 0) pr = *reinterpret_cast<const uint16_t*>(hal + 2 * (kIqHaloPairs + g));
+        else if (g < a.block_pairs) pr = *reinterpret_cast<const uint16_t*>(blk + 2 * (size_t)g);
+        else pr = 0x8080u;
+        sx[pad_pos<L>(u)] = make_float2(unpack_u8(pr & 0xFFu), unpack_u8(pr >> 8));
+    }
+    // carry the last pairs of this block to the next block's halo (one tile per stream does it)
+    if (tile == 0)
+        for (int i = threadIdx.x; i < kIqHaloPairs; i += kRfThreads)
+            reinterpret_cast<uint16_t*>(a.halo_out + (size_t)s * (2 * kIqHaloPairs))[i] =
+                *reinterpret_cast<const uint16_t*>(blk + 2 * (size_t)(a.block_pairs - kIqHaloPairs + i));
+    __syncthreads();
+    float2 acc[kRfR];
+#pragma unroll
+    for (int j = 0; j < kRfR; j++) acc[j] = make_float2(0.0f, 0.0f);
+    fir_core<DECIM, kRfR, float2>(sx + (L + 1) * threadIdx.x, taps, acc);
+#pragma unroll
+    for (int j = 0; j < kRfR; j++) sy[kRfR * threadIdx.x + j] = acc[j];
+    __syncthreads();
+    for (int q = threadIdx.x + 1; q < kRfTile; q += kRfThreads) {
+        int m = m0 + q;
+        if (m < a.if_block) {
+            float2 c = sy[q], p = sy[q - 1];
+            ring_store(a.fm, s, m, fm_discriminate(c.x, c.y, p.x, p.y));
+            if (a.i_ds) {
+                a.i_ds[(size_t)s * a.if_block + m] = c.x;
+                a.q_ds[(size_t)s * a.if_block + m] = c.y;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  IF band filters: NF 101-tap FIRs (decim 1) over one input ring, e.g. pilot / stereo / RDS
+// band-pass over fm_demod (/root/reference/src/stereo.cpp:74,80, src/rds.cpp:105), the 114 kHz
+// band-pass over rds_band^2 (src/rds.cpp:111-116, SQUARE) and the RRC.  One warp = one tile of 256
+// outputs of one stream.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBankR = 8;
+constexpr int kBankTile = 32 * kBankR;
+constexpr int kBankWarps = 4;
+
+template <int NF>
+struct BankArgs {
+    const float* x;  // input ring slot, sample 0 of stream 0 (halo >= kState)
+    size_t x_pitch;
+    int n;           // samples per block
+    int tiles;       // tiles per stream
+    int n_streams;
+    RingView y[NF];
+    Taps101 taps[NF];
+};
+
+template <int NF, bool SQUARE>
+__global__ void __launch_bounds__(32 * kBankWarps) k_fir_bank(const __grid_constant__ BankArgs<NF> a) {
+    constexpr int NS = kBankTile + kState;
+    __shared__ float sx[kBankWarps][NS + NS / kBankR + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * kBankWarps + warp;
+    const int s = (int)(wid / a.tiles);
+    const int tile = (int)(wid % a.tiles);
+    if (s >= a.n_streams) return;
+    const int n0 = tile * kBankTile;
+    const float* xr = a.x + (size_t)s * a.x_pitch + n0 - kState;
+    for (int u = lane; u < NS; u += 32) {
+        float v = (n0 - kState + u < a.n) ? xr[u] : 0.0f;
+        if (SQUARE) v = __fmul_rn(v, v);
+        sx[warp][pad_pos<kBankR>(u)] = v;
+    }
+    __syncwarp();
+    float acc[NF][kBankR];
+#pragma unroll
+    for (int f = 0; f < NF; f++)
+#pragma unroll
+        for (int j = 0; j < kBankR; j++) acc[f][j] = 0.0f;
+    fir_bank_core<NF, kBankR>(&sx[warp][(kBankR + 1) * lane], a.taps, acc);
+#pragma unroll
+    for (int f = 0; f < NF; f++)
+#pragma unroll
+        for (int j = 0; j < kBankR; j++) {
+            int n = n0 + kBankR * lane + j;
+            if (n < a.n) ring_store(a.y[f], s, n, acc[f][j]);
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  PLL: one lane per stream, strictly sequential in time.  /root/reference/src/pll.cpp:4-61.
+// The NCO output cos(trigArg*ncoScale + phaseAdjust) (:52) is not part of the recurrence, so the
+// kernel only stores trigArg; the consumers (k_mix, or the standalone ABI call) evaluate the cosine
+// in parallel.  blockIdx.y selects one of two independent loops (19 kHz pilot, 114 kHz RDS carrier).
+// ------------------------------------------------------------------------------------------------
+struct PllStateDev {
+    float feedbackI, feedbackQ, integrator, phaseEst;
+    double trigOffset;
+};
+
+struct PllLoop {
+    const float* x;  // input slot, sample 0 of stream 0
+    size_t x_pitch;
+    RingView trig;   // trig.cur[i] = trigArg after input sample i
+    PllStateDev* st; // [n_streams]
+    cr::PllCoef coef;
+};
+
+struct PllArgs {
+    PllLoop loop[2];
+    int n;
+    int n_streams;
+};
+
+constexpr int kPllThreads = 32;
+
+__global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
+    __shared__ cr::AtanTab tab;
+    {
+        const cr::AtanTab init = SDRB_ATAN_TAB_INIT;
+        if (threadIdx.x < 17) {
+            tab.hi[threadIdx.x] = init.hi[threadIdx.x];
+            tab.lo[threadIdx.x] = init.lo[threadIdx.x];
+        }
+    }
+    __syncthreads();
+    const PllLoop& lp = a.loop[blockIdx.y];
+    const int s = blockIdx.x * kPllThreads + threadIdx.x;
+    if (s >= a.n_streams) return;
+    PllStateDev sd = lp.st[s];
+    cr::PllState st{sd.feedbackI, sd.feedbackQ, sd.integrator, sd.phaseEst, sd.trigOffset};
+    const cr::PllCoef k = lp.coef;
+    const float* x = lp.x + (size_t)s * lp.x_pitch;
+    float* out = lp.trig.cur + (size_t)s * lp.trig.pitch;
+    const int n4 = a.n & ~3;
+    float4 nx = (n4 > 0) ? *reinterpret_cast<const float4*>(x) : make_float4(0, 0, 0, 0);
+    for (int i = 0; i < n4; i += 4) {
+        float4 c = nx;
+        if (i + 4 < n4) nx = *reinterpret_cast<const float4*>(x + i + 4);
+        float4 o;
+        o.x = cr::pll_step_trig(c.x, st, k, tab);
+        o.y = cr::pll_step_trig(c.y, st, k, tab);
+        o.z = cr::pll_step_trig(c.z, st, k, tab);
+        o.w = cr::pll_step_trig(c.w, st, k, tab);
+        *reinterpret_cast<float4*>(out + i) = o;
+    }
+    for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_trig(x[i], st, k, tab);
+    // tail -> halo of the next slot
+    float* nh = lp.trig.nxt + (size_t)s * lp.trig.pitch;
+    for (int b = 1; b <= lp.trig.halo && b <= a.n; b++) nh[-b] = out[a.n - b];
+    lp.st[s] = PllStateDev{st.feedbackI, st.feedbackQ, st.integrator, st.phaseEst, st.trigOffset};
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b  Mixers (elementwise, parallel): NCO cosines from the stored trigArg and the two products
+//   stereo_dc[i] = (float)(2.0 * stereo_band[i] * carrier[i])        /root/reference/src/stereo.cpp:83-85
+//   rds_dc[i]    = 2 * rds_band[i-50] * IPLL[i]   (float)              src/rds.cpp:122-127
+// carrier[i] / IPLL[i] is the NCO output after input sample i-1 (src/pll.cpp:18,52), i.e.
+// cos(ncoScale * trig[i-1] + phaseAdjust); trig[-1] of the very first block is 0 -> 1.0 (the seed the
+// callers put in pllOut[N], src/stereo.cpp:45, src/rds.cpp:38).
+// ------------------------------------------------------------------------------------------------
+struct MixArgs {
+    int n, n_streams;
+    // stereo
+    const float* band;  size_t band_pitch;
+    const float* trig19; size_t trig19_pitch;
+    RingView stereo_dc;
+    float* carrier_out;  // optional [n_streams][n+1]
+    // rds (rds_band == nullptr: skip)
+    const float* rds_band; size_t rds_band_pitch;
+    const float* trig114; size_t trig114_pitch;
+    RingView rds_dc;
+    float* ipll_out;     // optional [n_streams][n+1]
+    float* delay_out;    // optional rds_band_delay [n_streams][n]
+    float scale19, adjust19, scale114, adjust114;
+    int do_stereo;
+};
+
+__global__ void __launch_bounds__(256) k_mix(const MixArgs a) {
+    const int s = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > a.n) return;
+    if (a.do_stereo) {
+        float th = a.trig19[(size_t)s * a.trig19_pitch + i - 1];
+        float car = cr::cos_f(__fadd_rn(__fmul_rn(th, a.scale19), a.adjust19));
+        if (a.carrier_out) a.carrier_out[(size_t)s * (a.n + 1) + i] = car;
+        if (i < a.n) {
+            float b = a.band[(size_t)s * a.band_pitch + i];
+            float v = __double2float_rn(__dmul_rn(__dmul_rn(2.0, (double)b), (double)car));
+            ring_store(a.stereo_dc, s, i, v);
+        }
+    }
+    if (a.rds_band) {
+        float th = a.trig114[(size_t)s * a.trig114_pitch + i - 1];
+        float ip = cr::cos_f(__fadd_rn(__fmul_rn(th, a.scale114), a.adjust114));
+        if (a.ipll_out) a.ipll_out[(size_t)s * (a.n + 1) + i] = ip;
+        if (i < a.n) {
+            // the all-pass "delay" FIR (src/rds.cpp:122): 0 + 1*x[i-50] + 0*... == 0.0f + x[i-50]
+            float d = __fadd_rn(0.0f, a.rds_band[(size_t)s * a.rds_band_pitch + i - 50]);
+            if (a.delay_out) a.delay_out[(size_t)s * a.n + i] = d;
+            ring_store(a.rds_dc, s, i, __fmul_rn(__fmul_rn(2.0f, d), ip));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  Audio: 101-tap low-pass + decimate (up == 1 fast path) on mono and L-R, recombine, int16.
+// /root/reference/src/mono.cpp:34-42, src/stereo.cpp:88-107, src/filter.cpp:123-147.
+// ------------------------------------------------------------------------------------------------
+// float -> short exactly as the x86-64 reference build does it: cvttss2si (INT_MIN when out of
+// range or NaN), then the low 16 bits.
+__device__ __forceinline__ int16_t to_pcm(float v) {
+    int i = (v > -2147483904.0f && v < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000;
+    return (int16_t)(uint16_t)((uint32_t)i & 0xFFFFu);
+}
+
+struct AudioArgs {
+    const float* mono_x;  // ring slot of the mono path input, already offset by the delay (sample 0)
+    size_t mono_pitch;
+    const float* dc_x;    // stereo_dc ring slot (nullptr: mono only)
+    size_t dc_pitch;
+    int n_in;             // IF samples per block
+    int n_out;            // audio frames per block
+    int up, down;
+    const float* taps_pm; // generic path: phase-major taps [up][kTaps] (taps_pm[p*kTaps+j] = h[p + up*j])
+    int16_t* pcm;         // [n_streams][pcm_pitch]
+    size_t pcm_pitch;
+    float* mono_out;      // optional [n_streams][n_out]
+    float* dc_out;        // optional
+};
+
+constexpr int kAudR = 4;
+constexpr int kAudThreads = 64;
+constexpr int kAudTile = kAudR * kAudThreads;
+
+template <int DOWN, bool STEREO>
+__global__ void __launch_bounds__(kAudThreads) k_audio_decim(const __grid_constant__ Taps101 taps, const AudioArgs a) {
+    constexpr int L = DOWN * kAudR;
+    constexpr int NS = DOWN * (kAudTile - 1) + kTaps;
+    __shared__ float2 sx[NS + NS / L + 2];
+    const int s = blockIdx.y;
+    const int m0 = blockIdx.x * kAudTile;
+    const int g0 = DOWN * m0 - kState;
+    const float* mx = a.mono_x + (size_t)s * a.mono_pitch;
+    const float* dx = STEREO ? a.dc_x + (size_t)s * a.dc_pitch : nullptr;
+    for (int u = threadIdx.x; u < NS; u += kAudThreads) {
+        int g = g0 + u;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (g < a.n_in) {
+            // stereo(): mono goes through the all-pass delay FIR first == 0.0f + x (src/stereo.cpp:88);
+            // mono(): fed directly (src/mono.cpp:34).  Adding +0 is exact either way except for -0.
+            v.x = STEREO ? __fadd_rn(0.0f, mx[g]) : mx[g];
+            if (STEREO) v.y = dx[g];
+        }
+        sx[pad_pos<L>(u)] = v;
+    }
+    __syncthreads();
+    float2 acc[kAudR];
+#pragma unroll
+    for (int j = 0; j < kAudR; j++) acc[j] = make_float2(0.0f, 0.0f);
+    fir_core<DOWN, kAudR, float2>(sx + (L + 1) * threadIdx.x, taps, acc);
+    const int m = m0 + kAudR * threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < kAudR; j++) {
+        if (m + j < a.n_out) {
+            if (STEREO) {
+                int16_t* p = a.pcm + (size_t)s * a.pcm_pitch + 2 * (m + j);
+                p[0] = to_pcm(__fmul_rn(16384.0f, __fadd_rn(acc[j].x, acc[j].y)));   // left, even index
+                p[1] = to_pcm(__fmul_rn(16384.0f, __fadd_rn(acc[j].x, -acc[j].y)));  // right, odd index
+                if (a.mono_out) {
+                    a.mono_out[(size_t)s * a.n_out + m + j] = acc[j].x;
+                    a.dc_out[(size_t)s * a.n_out + m + j] = acc[j].y;
+                }
+            } else {
+                a.pcm[(size_t)s * a.pcm_pitch + m + j] = to_pcm(__fmul_rn(16384.0f, acc[j].x));
+                if (a.mono_out) a.mono_out[(size_t)s * a.n_out + m + j] = acc[j].x;
+            }
+        }
+    }
+}
+
+// Generic rational resampler (any up/down; used for up = 147).  One thread per output frame.
+// y[n] = sum_j h[phase + up*j] * x[(n*down - phase)/up - j],  phase = (n*down) % up.
+template <bool STEREO>
+__global__ void __launch_bounds__(128) k_audio_updown(const AudioArgs a) {
+    const int s = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.n_out) return;
+    const long long nd = (long long)n * a.down;
+    const int phase = (int)(nd % a.up);
+    const int base = (int)(nd / a.up);
+    const float* h = a.taps_pm + (size_t)phase * kTaps;
+    const float* mx = a.mono_x + (size_t)s * a.mono_pitch + base;
+    const float* dx = STEREO ? a.dc_x + (size_t)s * a.dc_pitch + base : nullptr;
+    float am = 0.0f, ad = 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < kTaps; j++) {
+        float hj = __ldg(h + j);
+        float xm = STEREO ? __fadd_rn(0.0f, mx[-j]) : mx[-j];
+        am = mac(am, hj, xm);
+        if (STEREO) ad = mac(ad, hj, dx[-j]);
+    }
+    if (STEREO) {
+        int16_t* p = a.pcm + (size_t)s * a.pcm_pitch + 2 * n;
+        p[0] = to_pcm(__fmul_rn(16384.0f, __fadd_rn(am, ad)));
+        p[1] = to_pcm(__fmul_rn(16384.0f, __fadd_rn(am, -ad)));
+        if (a.mono_out) {
+            a.mono_out[(size_t)s * a.n_out + n] = am;
+            a.dc_out[(size_t)s * a.n_out + n] = ad;
+        }
+    } else {
+        a.pcm[(size_t)s * a.pcm_pitch + n] = to_pcm(__fmul_rn(16384.0f, am));
+        if (a.mono_out) a.mono_out[(size_t)s * a.n_out + n] = am;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  RDS back end, one CTA per stream: 247/640 resampler + 3 kHz LPF, RRC, clock recovery, slicer,
+// Manchester and differential decode, and (every 15 decode blocks) frame sync.
+// /root/reference/src/rds.cpp:130-189, src/rds_utilities.cpp:4-88,313-400.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRdsUp = 247, kRdsDown = 640;
+constexpr int kRdsThreads = 256;
+constexpr int kRdsMaxBits = 48;
+constexpr int kRdsMaxGroups = 8;
+constexpr int kBitBufWords = 26;  // 832 bits of storage; at most kBitBufCap are ever occupied
+constexpr int kBitBufCap = 704;    // 15 blocks x <= 38 bits + carried leftover (< 64) fits with room to spare
+
+struct RdsRecord {  // mirrors sdrb_rds_record
+    int32_t cdr_offset, n_symbols, n_bits, n_groups;
+    uint8_t bits[kRdsMaxBits];
+    uint64_t groups[kRdsMaxGroups];
+};
+
+struct RdsStreamState {
+    int32_t block_count;   // src/rds.cpp:28
+    int32_t decoder_cont;  // :32
+    int32_t half_symbol, start, last_bit;  // :29-31
+    int32_t nbits;         // bits waiting in bitbuf (carried leftover + this period's blocks)
+    int32_t window[4];     // last four matched offsets (0 A, 1 B, 2 C, 3 C', 4 D), src/rds.cpp:70
+    int32_t nwindow;
+    int32_t first_time;
+    uint64_t reg;          // :67
+    uint32_t bitbuf[kBitBufWords];  // bit i at word i/32, bit i%32
+};
+
+struct RdsArgs {
+    const float* dc;       // rds_dc ring slot (halo >= kState)
+    size_t dc_pitch;
+    int n_in;              // IF samples per block
+    int n_out;             // n_in*247/640
+    int sps;
+    int rds_on;
+    const float* taps_perm;  // [kTaps][256]: taps_perm[j*256 + t] = h_lpf[(146*t % 247) + 247*j]  (t < 247)
+    Taps101 rrc;
+    float* filt_state_in;    // [n_streams][kState] last rds_filt samples of the previous block
+    float* filt_state_out;
+    RdsStreamState* st;      // [n_streams]
+    RdsRecord* rec;          // [n_streams]
+    float* filt_out;         // optional [n_streams][n_out]
+    float* clean_out;        // optional
+};
+
+// check_block's syndrome test (/root/reference/src/rds_utilities.cpp:357-366) on a 26-bit window held
+// LSB-first (bit t = t-th received bit).  Masks are the parity_matrix rows of :122-133, the syndromes
+// those of :135, both re-packed LSB-first.  Returns 0 A, 1 B, 2 C, 3 C', 4 D, -1 none.
+__device__ __forceinline__ int rds_block_type(uint32_t w) {
+    constexpr uint32_t rows[10] = {0x39BE401u, 0x337C802u, 0x1F47404u, 0x0730C08u, 0x0E61810u,
+                                   0x257D420u, 0x3344C40u, 0x1F37C80u, 0x3E6F900u, 0x3CDF200u};
+    uint32_t syn = 0;
+#pragma unroll
+    for (int c = 0; c < 10; c++) syn |= (uint32_t)(__popc(w & rows[c]) & 1) << c;
+    int t = -1;
+    if (syn == 0x06Fu) t = 0;
+    if (syn == 0x0AFu) t = 1;
+    if (syn == 0x0E9u) t = 2;
+    if (syn == 0x0CFu) t = 3;
+    if (syn == 0x069u) t = 4;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t bitbuf_window26(const uint32_t* buf, int idx) {
+    int w = idx >> 5, sh = idx & 31;
+    uint64_t two = (uint64_t)buf[w] | ((uint64_t)buf[w + 1] << 32);
+    return (uint32_t)(two >> sh) & 0x3FFFFFFu;
+}
+
+constexpr int kRrcR = 12;
+constexpr int kRrcTile = kRrcR * kRdsThreads;  // 3072 outputs per pass
+constexpr int kResQ = 12;                      // resampler outputs per thread per pass
+
+__global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_constant__ RdsArgs a) {
+    extern __shared__ float smem[];
+    const int s = blockIdx.x;
+    const int t = threadIdx.x;
+    const int n_in = a.n_in, n_out = a.n_out;
+    const int rrc_tiles = (n_out + kRrcTile - 1) / kRrcTile;
+    const int nfilt_pad = rrc_tiles * kRrcTile + kState;
+    float* sdc = smem;                                // [n_in + kState]; later reused as sclean [n_out]
+    float* sfilt = smem + (n_in + kState + 3) / 4 * 4;  // padded layout, pad_pos<kRrcR>
+    __shared__ int ssum[64];
+    __shared__ int ssym[160];
+    __shared__ int8_t stype[kBitBufWords * 32];
+    __shared__ int soff;
+
+    // ---- stage rds_dc (with the carried 100-sample state in front)
+    const float* dc = a.dc + (size_t)s * a.dc_pitch - kState;
+    for (int u = t; u < n_in + kState; u += kRdsThreads) sdc[u] = dc[u];
+    for (int u = t; u < kState; u += kRdsThreads)
+        sfilt[pad_pos<kRrcR>(u)] = a.filt_state_in[(size_t)s * kState + u];
+    for (int u = n_out + kState + t; u < nfilt_pad; u += kRdsThreads) sfilt[pad_pos<kRrcR>(u)] = 0.0f;
+    if (t < 64) ssum[t] = 0;
+    __syncthreads();
+
+    // ---- 247/640 resampler (/root/reference/src/filter.cpp:123-147, src/rds.cpp:130).
+    // Outputs n and n+247 share the polyphase branch, so thread t (< 247) owns n = t + 247 q and keeps
+    // its 101 branch taps h[phase + 247 j] in flight once per pass over q.
+    if (t < kRdsUp) {
+        const int base = (kRdsDown * t) / kRdsUp;  // (n*down - phase)/up for q = 0
+        for (int q0 = 0; q0 * kRdsUp + t < n_out; q0 += kResQ) {
+            float acc[kResQ];
+            int off[kResQ];
+#pragma unroll
+            for (int qq = 0; qq < kResQ; qq++) {
+                acc[qq] = 0.0f;
+                int n = (q0 + qq) * kRdsUp + t;
+                off[qq] = (n < n_out) ? kRdsDown * (q0 + qq) + base + kState : kState;
+            }
+            for (int j = 0; j < kTaps; j++) {
+                const float hj = __ldg(a.taps_perm + j * 256 + t);
+#pragma unroll
+                for (int qq = 0; qq < kResQ; qq++) acc[qq] = mac(acc[qq], hj, sdc[off[qq] - j]);
+            }
+#pragma unroll
+            for (int qq = 0; qq < kResQ; qq++) {
+                int n = (q0 + qq) * kRdsUp + t;
+                if (n < n_out) {
+                    sfilt[pad_pos<kRrcR>(n + kState)] = acc[qq];
+                    if (a.filt_out) a.filt_out[(size_t)s * n_out + n] = acc[qq];
+                    if (n >= n_out - kState) a.filt_state_out[(size_t)s * kState + (n - (n_out - kState))] = acc[qq];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- RRC matched filter (src/rds.cpp:133), 12 consecutive outputs per thread
+    float* sclean = sdc;
+    for (int tile = 0; tile < rrc_tiles; tile++) {
+        float acc[kRrcR];
+#pragma unroll
+        for (int j = 0; j < kRrcR; j++) acc[j] = 0.0f;
+        fir_core<1, kRrcR, float>(sfilt + pad_pos<kRrcR>(tile * kRrcTile) + (kRrcR + 1) * t, a.rrc, acc);
+#pragma unroll
+        for (int j = 0; j < kRrcR; j++) {
+            int n = tile * kRrcTile + kRrcR * t + j;
+            if (n < n_out) {
+                sclean[n] = acc[j];
+                if (a.clean_out) a.clean_out[(size_t)s * n_out + n] = acc[j];
+            }
+        }
+    }
+    __syncthreads();
+
+    RdsStreamState* st = a.st + s;
+    RdsRecord* rec = a.rec + s;
+    const int block_count = st->block_count;
+    const bool decode = block_count > 5 && a.rds_on;  // src/rds.cpp:135
+    if (!decode) {
+        if (t == 0) {
+            rec->cdr_offset = -1; rec->n_symbols = 0; rec->n_bits = 0; rec->n_groups = 0;
+            st->block_count = block_count + 1;
+        }
+        return;
+    }
+    // carried decoder state, read by every thread before the barriers below (lane 0 rewrites it at the end)
+    const int start_in = st->start, half_in = st->half_symbol, last_in = st->last_bit;
+    const int nbits_in = st->nbits, decoder_cont_in = st->decoder_cont;
+
+    // ---- clock recovery: argmax over the sps sampling phases of sum |(int)x| (src/rds_utilities.cpp:4-21)
+    const int sps = a.sps;
+    {
+        const int parts = kRdsThreads / sps;
+        const int i = t % sps, part = t / sps;
+        const int nk = n_out / sps;
+        if (part < parts) {
+            int sum = 0;
+            for (int k = part; k < nk; k += parts) sum += abs(__float2int_rz(sclean[k * sps + i]));
+            atomicAdd(&ssum[i], sum);
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        int maxi = 0, maxv = 0;
+        for (int i = 0; i < sps; i++)
+            if (ssum[i] > maxv) { maxv = ssum[i]; maxi = i; }
+        soff = maxi;
+    }
+    __syncthreads();
+    const int off = soff;
+    const int nsym = (n_out - off + sps - 1) / sps;  // src/rds.cpp:157-161
+    if (t < nsym && t < 160) ssym[t] = sclean[off + t * sps] > 0.0f;
+    __syncthreads();
+    if (t >= 32) return;
+
+    // ---- warp 0: Manchester pairing (src/rds_utilities.cpp:34-68) as two ballots, differential decode
+    // (:70-88) as one shifted XOR on the 64-bit word.
+    int nb = start_in + ((nsym - 1 - start_in) > 0 ? (nsym - 1 - start_in + 1) / 2 : 0);
+    if (nb > kRdsMaxBits) nb = kRdsMaxBits;
+    uint32_t wlo, whi;
+    {
+        int q = t, bit = 0;
+        if (q < nb) bit = (start_in && q == 0) ? half_in : ssym[start_in + 2 * (q - start_in)];
+        wlo = __ballot_sync(0xFFFFFFFFu, bit != 0);
+        q = t + 32; bit = 0;
+        if (q < nb) bit = ssym[start_in + 2 * (q - start_in)];
+        whi = __ballot_sync(0xFFFFFFFFu, bit != 0);
+    }
+    const uint64_t W = (uint64_t)wlo | ((uint64_t)whi << 32);
+    const uint64_t Dm = (W ^ ((W << 1) | (uint64_t)(last_in & 1))) & (nb >= 64 ? ~0ull : ((1ull << nb) - 1));
+    for (int q = t; q < kRdsMaxBits; q += 32) rec->bits[q] = (q < nb) ? (uint8_t)((Dm >> q) & 1) : 0;
+
+    int nbits = nbits_in;
+    int decoder_cont = decoder_cont_in + 1;
+    if (t == 0) {
+        // carried symbol state (:61-66), last bit (:87)
+        if (((unsigned)nsym - (unsigned)start_in) & 1u) { st->half_symbol = ssym[nsym - 1]; st->start = 1; }
+        else st->start = 0;
+        if (nb > 0) st->last_bit = (int)((W >> (nb - 1)) & 1);
+        // append to the stream buffer (src/rds.cpp:182)
+        if (nbits + nb <= kBitBufCap) {
+            int w = nbits >> 5, sh = nbits & 31;
+            uint64_t lo = Dm << sh;
+            st->bitbuf[w] = (st->bitbuf[w] & ((1u << sh) - 1u)) | (uint32_t)lo;
+            st->bitbuf[w + 1] = (uint32_t)(lo >> 32);
+            st->bitbuf[w + 2] = sh ? (uint32_t)(Dm >> (64 - sh)) : 0u;
+            nbits += nb;
+        }
+        rec->cdr_offset = off; rec->n_symbols = nsym; rec->n_bits = nb;
+    }
+    nbits = __shfl_sync(0xFFFFFFFFu, nbits, 0);
+    __syncwarp();
+
+    int ngroups = 0;
+    if (decoder_cont == 15) {  // src/rds.cpp:184-189 -> start_frame_sync, src/rds_utilities.cpp:384-400
+        decoder_cont = 0;
+        const int total = nbits;
+        const int end_range = total >= 26 ? total - 26 : 0;  // idx < size-26: the last full window waits
+        for (int idx = t; idx < end_range; idx += 32) stype[idx] = (int8_t)rds_block_type(bitbuf_window26(st->bitbuf, idx));
+        __syncwarp();
+        if (t == 0) {
+            uint64_t reg = st->reg;
+            int win[4] = {st->window[0], st->window[1], st->window[2], st->window[3]};
+            int nwin = st->nwindow;
+            int idx = 0;
+            while (idx < end_range) {
+                int ty = stype[idx];
+                if (ty >= 0) {
+                    if (ty != 3) {  // "Cp" matches but copies nothing (:370)
+                        int bt = (ty == 4) ? 3 : ty;
+                        uint64_t word = (uint64_t)((__brev(bitbuf_window26(st->bitbuf, idx)) >> 16) & 0xFFFFu);
+                        int shl = 48 - 16 * bt;
+                        reg = (reg & ~((uint64_t)0xFFFF << shl)) | (word << shl);
+                    }
+                    if (nwin == 4) { win[0] = win[1]; win[1] = win[2]; win[2] = win[3]; nwin = 3; }
+                    win[nwin++] = ty;
+                    if (nwin == 4 && win[0] == 0 && win[1] == 1 && win[2] == 2 && win[3] == 4) {
+                        if (ngroups < kRdsMaxGroups) rec->groups[ngroups] = reg;
+                        ngroups++;
+                        st->first_time = 0;
+                    }
+                    idx += 26;
+                } else {
+                    idx += 1;
+                }
+            }
+            st->reg = reg;
+            st->window[0] = win[0]; st->window[1] = win[1]; st->window[2] = win[2]; st->window[3] = win[3];
+            st->nwindow = nwin;
+            // keep the unread tail as the carry (:398-399): shift the buffer down by idx bits
+            int keep = total - idx;
+            if (keep < 0) keep = 0;
+            uint32_t tmp[kBitBufWords];
+            int w0 = idx >> 5, sh = idx & 31;
+            for (int w = 0; w < kBitBufWords; w++) {
+                uint32_t lo = (w0 + w < kBitBufWords) ? st->bitbuf[w0 + w] : 0u;
+                uint32_t hi = (w0 + w + 1 < kBitBufWords) ? st->bitbuf[w0 + w + 1] : 0u;
+                tmp[w] = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+            }
+            for (int w = 0; w < kBitBufWords; w++) {
+                int lim = keep - 32 * w;
+                uint32_t m = lim >= 32 ? 0xFFFFFFFFu : (lim <= 0 ? 0u : ((1u << lim) - 1u));
+                st->bitbuf[w] = tmp[w] & m;
+            }
+            nbits = keep;
+        }
+    }
+    if (t == 0) {
+        rec->n_groups = ngroups < kRdsMaxGroups ? ngroups : kRdsMaxGroups;
+        st->nbits = nbits;
+        st->decoder_cont = decoder_cont;
+        st->block_count = block_count + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone batched primitives behind the per-function ABI (sdrb_fir_decim, sdrb_fir_updown,
+// sdrb_fm_demod, sdrb_pll, sdrb_cdr).  Straightforward one-thread-per-output kernels: they serve the
+// std::vector shim (batch = 1 drop-in use) and cross-check the fused kernels; the chain does not use them.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fir_decim_generic(const float* x, size_t x_pitch, int nx, const float* h, int nh, const float* state,
+                                    int nstate, float* y, size_t y_pitch, int decim) {
+    const int s = blockIdx.y;
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nx / decim) return;
+    const float* xs = x + (size_t)s * x_pitch;
+    const float* ss = state + (size_t)s * nstate;
+    const int n = m * decim;
+    float acc = 0.0f;
+    for (int k = 0; k < nh; k++) {
+        int j = n - k;
+        float xv = (j < 0) ? ((j + nstate >= 0) ? ss[j + nstate] : 0.0f) : xs[j];
+        acc = mac(acc, __ldg(h + k), xv);
+    }
+    y[(size_t)s * y_pitch + m] = acc;
+}
+
+__global__ void k_fir_updown_generic(const float* x, size_t x_pitch, int nx, const float* h, int nh, const float* state,
+                                     int nstate, float* y, size_t y_pitch, int up, int down) {
+    const int s = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (int)(((long long)nx * up) / down)) return;
+    const float* xs = x + (size_t)s * x_pitch;
+    const float* ss = state + (size_t)s * nstate;
+    const long long nd = (long long)n * down;
+    const int phase = (int)(nd % up);
+    float acc = 0.0f;
+    for (int k = phase; k < nh; k += up) {
+        int xi = (int)((nd - k) / up);
+        float xv = (xi < 0) ? ((xi + nstate >= 0) ? ss[xi + nstate] : 0.0f) : xs[xi];
+        acc = mac(acc, __ldg(h + k), xv);
+    }
+    y[(size_t)s * y_pitch + n] = acc;
+}
+
+// state <- last nstate inputs (src/filter.cpp:119,145); runs after the FIR kernel on the same stream
+__global__ void k_state_update(const float* x, size_t x_pitch, int nx, float* state, int nstate) {
+    const int s = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nstate) return;
+    float* ss = state + (size_t)s * nstate;
+    const float* xs = x + (size_t)s * x_pitch;
+    // nx >= nstate at every reference call site; otherwise the old state slides (done out of place by
+    // the caller passing nx < nstate is rejected on the host side)
+    ss[i] = xs[nx - nstate + i];
+}
+
+__global__ void k_fm_demod_generic(const float* I, const float* Q, size_t pitch, int n, const float* prev, float* out,
+                                   size_t out_pitch) {
+    const int s = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* Is = I + (size_t)s * pitch;
+    const float* Qs = Q + (size_t)s * pitch;
+    float pI = i ? Is[i - 1] : prev[2 * s], pQ = i ? Qs[i - 1] : prev[2 * s + 1];
+    out[(size_t)s * out_pitch + i] = fm_discriminate(Is[i], Qs[i], pI, pQ);
+}
+__global__ void k_fm_prev_update(const float* I, const float* Q, size_t pitch, int n, float* prev, int n_streams) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams || n <= 0) return;
+    prev[2 * s] = I[(size_t)s * pitch + n - 1];
+    prev[2 * s + 1] = Q[(size_t)s * pitch + n - 1];
+}
+
+struct PllStateAbi {  // mirrors sdrb_pll_state
+    float feedbackI, feedbackQ, integrator, phaseEst;
+    double trigOffset;
+    float lastCarrier;
+    float last_out;
+};
+
+__global__ void __launch_bounds__(kPllThreads) k_pll_generic(const float* in, size_t in_pitch, int n, cr::PllCoef k,
+                                                              PllStateAbi* stp, float* out, size_t out_pitch, int n_streams) {
+    __shared__ cr::AtanTab tab;
+    {
+        const cr::AtanTab init = SDRB_ATAN_TAB_INIT;
+        if (threadIdx.x < 17) {
+            tab.hi[threadIdx.x] = init.hi[threadIdx.x];
+            tab.lo[threadIdx.x] = init.lo[threadIdx.x];
+        }
+    }
+    __syncthreads();
+    const int s = blockIdx.x * kPllThreads + threadIdx.x;
+    if (s >= n_streams) return;
+    PllStateAbi sa = stp[s];
+    cr::PllState st{sa.feedbackI, sa.feedbackQ, sa.integrator, sa.phaseEst, sa.trigOffset};
+    const float* x = in + (size_t)s * in_pitch;
+    float* o = out + (size_t)s * out_pitch;
+    o[0] = sa.last_out;  // src/pll.cpp:18
+    float last = sa.last_out;
+    for (int i = 0; i < n; i++) {
+        float th = cr::pll_step_trig(x[i], st, k, tab);
+        last = cr::cos_f(__fadd_rn(__fmul_rn(th, k.ncoScale), k.phaseAdjust));
+        o[i + 1] = last;
+    }
+    stp[s] = PllStateAbi{st.feedbackI, st.feedbackQ, st.integrator, st.phaseEst, st.trigOffset, last, last};
+}
+
+__global__ void __launch_bounds__(64) k_cdr_generic(const float* x, size_t x_pitch, int n, int sps, int* offset) {
+    __shared__ int ssum[64];
+    const int s = blockIdx.x;
+    const float* xs = x + (size_t)s * x_pitch;
+    int best = 0, bestv = 0;
+    for (int i0 = 0; i0 < sps; i0 += 64) {
+        int i = i0 + threadIdx.x;
+        int sum = 0;
+        if (i < sps)
+            for (int k = 0; k < n / sps; k++) sum += abs(__float2int_rz(xs[k * sps + i]));
+        ssum[threadIdx.x] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int j = 0; j < 64 && i0 + j < sps; j++)
+                if (ssum[j] > bestv) { bestv = ssum[j]; best = i0 + j; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offset[s] = best;
+}
+
+}  // namespace sdrb

@@ -1,0 +1,148 @@
+"""Parity of the CUDA receive chain (through the C ABI) against the oracle, bit for bit.
+
+Every comparison is exact: u8 unpack, decimation indexing, every float32 intermediate, the int16 PCM,
+CDR offsets, symbols, RDS bits, group registers and the stderr text (the float
+tolerance of 1e-4 the north star allows is not needed because the chain reproduces the reference's
+operation order and its libm roundings).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from chain_compare import FLOAT_STAGES, RDS_KEYS, diff_report, run_cuda_chain
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_same(got, want, keys, what):
+    rep = diff_report(got, want, keys)
+    bad = {k: v for k, v in rep.items() if v is not None}
+    assert not bad, f"{what}: stages that differ from the oracle: {bad}"
+
+
+@pytest.mark.parametrize("mode,kind,nblocks", [(0, "r", 40), (0, "s", 12), (0, "m", 12), (2, "m", 10), (1, "s", 8),
+                                               (1, "m", 6), (3, "m", 6), (2, "s", 6), (3, "s", 5)])
+def test_single_stream_all_stages(capi, oracle, station_iq, mode, kind, nblocks):
+    iq = station_iq(0, mode, nblocks)
+    stages = FLOAT_STAGES[kind]
+    got = run_cuda_chain(capi, mode, kind, [iq], nblocks, stages=stages)[0]
+    want = oracle.chain(mode, kind, iq, stages=stages)
+    _assert_same(got, want, ["pcm"] + stages + (RDS_KEYS if kind == "r" else []), f"mode {mode} {kind}")
+    if kind == "r":
+        assert len(want["groups"]) >= 5, "the synthetic station must decode RDS groups for this test to mean anything"
+        assert b"PI: 1234" in bytes(got["text"]) and b"PTY: Rock" in bytes(got["text"])
+
+
+def test_long_run_rds_text(capi, oracle, station_iq):
+    """130 blocks (4 s): the PS name appears and every bit and group matches."""
+    nblocks = 130
+    iq = station_iq(0, 0, nblocks)
+    got = run_cuda_chain(capi, 0, "r", [iq], nblocks)[0]
+    want = oracle.chain(0, "r", iq)
+    _assert_same(got, want, ["pcm"] + RDS_KEYS, "mode 0 r, 130 blocks")
+    assert b"Program Service: B200-SDR" in bytes(got["text"])
+
+
+def test_batch_equals_single_streams(capi, oracle, station_iq):
+    """Stream k of a ragged batch (33 streams: one full warp of PLL lanes plus one) == its own oracle run."""
+    nblocks, S = 10, 33
+    iqs = [station_iq(k % 5, 0, nblocks) for k in range(S)]
+    got = run_cuda_chain(capi, 0, "r", iqs, nblocks, pitch_pad=64)
+    wants = {k: oracle.chain(0, "r", station_iq(k, 0, nblocks)) for k in range(5)}
+    for s in range(S):
+        _assert_same(got[s], wants[s % 5], ["pcm"] + RDS_KEYS, f"stream {s}")
+
+
+def test_device_input_and_unpadded_pitch(capi, oracle, station_iq):
+    torch = pytest.importorskip("torch")
+    assert torch.cuda.is_available()
+    nblocks = 8
+    iq = station_iq(1, 0, nblocks)
+    got = run_cuda_chain(capi, 0, "s", [iq, iq], nblocks, device_input=True)
+    want = oracle.chain(0, "s", iq)
+    for s in range(2):
+        _assert_same(got[s], want, ["pcm"], f"device input stream {s}")
+
+
+def test_overlap_mode_matches(capi, oracle, station_iq):
+    nblocks = 24
+    iq = station_iq(2, 0, nblocks)
+    got = run_cuda_chain(capi, 0, "r", [iq] * 3, nblocks, overlap=True)
+    want = oracle.chain(0, "r", iq)
+    for s in range(3):
+        _assert_same(got[s], want, ["pcm"] + RDS_KEYS, f"overlap stream {s}")
+
+
+def test_state_save_load_resumes_bit_exact(capi, oracle, station_iq):
+    nblocks, cut = 24, 11
+    iq = station_iq(0, 0, nblocks)
+    want = oracle.chain(0, "r", iq)
+    bb = None
+    pcm, bits = [], []
+    with capi.Chain(0, "r", n_streams=2) as a:
+        bb = a.info.block_bytes
+        for b in range(cut):
+            blk = np.stack([iq[b * bb:(b + 1) * bb]] * 2)
+            a.process_host(blk)
+            pcm.append(a.read_pcm()[1].copy())
+            r = a.read_rds()[1]
+            bits.append(r["bits"][: r["n_bits"]].astype(np.int32))
+        blob = a.state_save()
+    with capi.Chain(0, "r", n_streams=2) as c2:
+        c2.state_load(blob)
+        for b in range(cut, nblocks):
+            blk = np.stack([iq[b * bb:(b + 1) * bb]] * 2)
+            c2.process_host(blk)
+            pcm.append(c2.read_pcm()[1].copy())
+            r = c2.read_rds()[1]
+            bits.append(r["bits"][: r["n_bits"]].astype(np.int32))
+    assert np.array_equal(np.concatenate(pcm), want["pcm"])
+    assert np.array_equal(np.concatenate(bits), want["rds_bits"])
+
+
+def test_edge_inputs(capi, oracle):
+    """All-128 input (I = Q = 0: the discriminator's guarded branch), all-0, all-255 and white noise."""
+    rng = np.random.default_rng(7)
+    bp = 73500
+    for name, iq in (("zeros128", np.full(2 * bp * 3, 128, np.uint8)), ("min", np.zeros(2 * bp * 3, np.uint8)),
+                     ("max", np.full(2 * bp * 3, 255, np.uint8)), ("noise", rng.integers(0, 256, 2 * bp * 8, dtype=np.uint8))):
+        nblocks = iq.size // (2 * bp)
+        stages = FLOAT_STAGES["r"]
+        got = run_cuda_chain(capi, 0, "r", [iq], nblocks, stages=stages)[0]
+        want = oracle.chain(0, "r", iq, stages=stages)
+        _assert_same(got, want, ["pcm"] + stages + RDS_KEYS, name)
+
+
+def test_golden_fixture(capi):
+    """The committed fixture (made from the unmodified reference sources, tests/golden/make_golden.py)."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "chain_m0_r.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden fixture missing")
+    z = np.load(path)
+    from conftest import load_module
+    gen = load_module("sdrgen", "real-time-sdr_b200/sdrgen.py")
+    nblocks = int(z["nblocks"])
+    iq = gen.generate_iq(gen.Station(), gen.block_pairs(0) * nblocks)
+    got = run_cuda_chain(capi, 0, "r", [iq], nblocks, stages=["fm_demod", "carrier", "rds_clean"])[0]
+    assert np.array_equal(got["pcm"], z["pcm"])
+    assert np.array_equal(got["rds_bits"], z["rds_bits"])
+    assert np.array_equal(got["groups"], z["groups"])
+    assert np.array_equal(got["cdr_offset"], z["cdr_offset"])
+    for st in ("fm_demod", "carrier", "rds_clean"):
+        sl = z[st + "_slice"]
+        off = int(z[st + "_offset"])
+        assert got[st][off:off + sl.size].tobytes() == sl.tobytes(), st
+
+
+def test_errors_are_reported_not_fatal(capi):
+    with pytest.raises(capi.SdrError):
+        capi.Chain(2, "r", 1)          # RDS is only defined for the 240 kHz IF (mode 0)
+    with capi.Chain(0, "m", 1) as ch:
+        with pytest.raises(capi.SdrError):
+            ch.read_pcm()              # nothing processed yet
+        with pytest.raises(capi.SdrError):
+            ch.read_rds()              # no RDS in a mono chain
+        with pytest.raises(capi.SdrError):
+            ch.process_host(np.zeros((1, 100), np.uint8), 100)  # pitch smaller than a block

@@ -1,0 +1,103 @@
+"""real-time-sdr_b200/csrc/pllmath.cuh (host build): the correctly-rounded float sin/cos/atan2 used by the
+PLL kernels must equal (float)glibc_double_fn((double)x), which is what the reference computes
+(/root/reference/src/pll.cpp:39,49,50,52).  The device build runs the same IEEE operations."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def host(_built):
+    L = C.CDLL(os.path.join(ROOT, "build", "libpllmath_host.so"))
+    L.crh_sincos.argtypes = [f32p, C.c_int, f32p, f32p]
+    L.crh_cos.argtypes = [f32p, C.c_int, f32p]
+    L.crh_atan2.argtypes = [f32p, f32p, C.c_int, f32p]
+    L.crh_sincos_tier.argtypes = [f32p, C.c_int, C.c_int, f32p, f32p]
+    L.crh_atan2_tier.argtypes = [f32p, f32p, C.c_int, C.c_int, f32p]
+    L.crh_scan_sincos.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+    L.crh_scan_atan2.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    L.crh_pll.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, f32p, f32p, C.POINTER(C.c_double)]
+    return L
+
+
+def test_sincos_scan_against_glibc(host):
+    """Every 257th float bit pattern from 2^-40 up to 3e9 (plus the negative mirror via symmetry of the code path)."""
+    out = (C.c_uint64 * 6)()
+    host.crh_scan_sincos(0x2B800000, 0x4F32D05E, 257, 8, out)
+    assert out[5] > 2_000_000
+    assert out[0] == 0 and out[1] == 0, f"sin/cos mismatches vs glibc: {out[0]}/{out[1]}, first pattern {out[3]:#x}"
+    assert out[2] < out[5] * 1e-4, "the slow tier should be rare"
+
+
+def test_sincos_dense_in_nco_range(host):
+    """Dense scan of the range the 19 kHz NCO phase lives in during the first seconds."""
+    out = (C.c_uint64 * 6)()
+    host.crh_scan_sincos(0x47000000, 0x47400000, 1, 8, out)  # 32768 .. 49152, every float
+    assert out[0] == 0 and out[1] == 0
+
+
+def test_sincos_special_values(host):
+    t = np.array([0.0, -0.0, 1e-30, -1e-30, 1.5707964, 3.1415927, 6.2831855, 1e-45, 2.5e9, -2.5e9, 4e9, np.inf, np.nan], np.float32)
+    s, c = np.zeros_like(t), np.zeros_like(t)
+    host.crh_sincos(t, t.size, s, c)
+    with np.errstate(invalid="ignore"):
+        ws, wc = np.sin(t.astype(np.float64)).astype(np.float32), np.cos(t.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(s.view(np.uint32)[:-2], ws.view(np.uint32)[:-2])
+    assert np.array_equal(c.view(np.uint32)[:-2], wc.view(np.uint32)[:-2])
+    assert np.isnan(s[-1]) and np.isnan(s[-2]) and np.isnan(c[-1])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_atan2_random_against_glibc(host, mode):
+    out = (C.c_uint64 * 6)()
+    host.crh_scan_atan2(12345 + mode, 1_500_000, mode, 8, out)
+    assert out[2] == 12_000_000
+    assert out[0] == 0, f"{out[0]} atan2 mismatches vs glibc, first y={out[3]:#x} x={out[4]:#x}"
+
+
+def test_atan2_special_values(host):
+    y = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 1.0, 1e-38, 1e-45, 3e38, 1.0, 0.5], np.float32)
+    x = np.array([1.0, 1.0, -1.0, -1.0, 0.0, 0.0, -0.0, 1e38, 1.0, 1e-38, 1.0, -0.5], np.float32)
+    o = np.zeros_like(y)
+    host.crh_atan2(y, x, y.size, o)
+    w = np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(o.view(np.uint32), w.view(np.uint32)), (o, w)
+
+
+def test_slow_tier_alone_is_also_exact(host):
+    rng = np.random.default_rng(9)
+    t = (rng.random(200000) * 3e6).astype(np.float32)
+    s, c = np.zeros_like(t), np.zeros_like(t)
+    host.crh_sincos_tier(t, t.size, 1, s, c)
+    assert np.array_equal(s, np.sin(t.astype(np.float64)).astype(np.float32))
+    assert np.array_equal(c, np.cos(t.astype(np.float64)).astype(np.float32))
+    y = (rng.standard_normal(200000) * 0.01).astype(np.float32)
+    x = (rng.standard_normal(200000) * 0.01).astype(np.float32)
+    o = np.zeros_like(y)
+    host.crh_atan2_tier(y, x, y.size, 1, o)
+    assert np.array_equal(o, np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(np.float32))
+
+
+@pytest.mark.parametrize("name,outn,freq,scale,bw", [("pilot", "carrier", 19e3, 2.0, 0.01), ("gen_pilot", "IPLL", 114e3, 0.5, 0.001)])
+def test_pll_recurrence_equals_oracle(host, oracle, station_iq, name, outn, freq, scale, bw):
+    """The PLL built from pll_step (what the CUDA kernels run) against the oracle's fmpll on real chain signals."""
+    nblocks, n = 60, 7350
+    a = oracle.chain(0, "r", station_iq(0, 0, nblocks), stages=(name, outn))
+    x = a[name]
+    out = np.zeros(n + 1, np.float32)
+    out[n] = 1
+    st = np.array([1, 0, 0, 0], np.float32)
+    trig = C.c_double(0)
+    ys = []
+    for b in range(nblocks):
+        host.crh_pll(x[b * n:(b + 1) * n], n, freq, 240000.0, scale, 0.0, bw, out, st, C.byref(trig))
+        ys.append(out.copy())
+    y = np.concatenate(ys)
+    assert int((y.view(np.uint32) != a[outn].view(np.uint32)).sum()) == 0
