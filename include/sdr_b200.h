@@ -138,6 +138,10 @@ int sdrb_chain_sync(sdrb_chain* c);
  * 0: every kernel of a block is issued on one stream, in order. */
 int sdrb_chain_set_overlap(sdrb_chain* c, int on);
 
+/* Issue this chain's work on the caller's CUDA stream (e.g. the application's or torch's current stream)
+ * instead of the private stream created by sdrb_chain_create.  Call between blocks only. */
+int sdrb_chain_set_stream(sdrb_chain* c, void* stream);
+
 /* Page-locked host memory for process_host / read_* buffers (cudaHostAlloc / cudaFreeHost). */
 int sdrb_pinned_alloc(size_t bytes, void** h_ptr);
 int sdrb_pinned_free(void* h_ptr);

@@ -25,7 +25,7 @@ EXPORTS = [
     "sdrb_chain_pcm_device", "sdrb_chain_read_rds", "sdrb_rds_parse", "sdrb_chain_stage",
     "sdrb_chain_state_bytes", "sdrb_chain_state_save", "sdrb_chain_state_load", "sdrb_chain_kernel_times",
     "sdrb_chain_set_profiling", "sdrb_chain_launch_count", "sdrb_chain_set_overlap", "sdrb_pinned_alloc",
-    "sdrb_pinned_free",
+    "sdrb_pinned_free", "sdrb_chain_set_stream",
 ]
 
 
@@ -108,6 +108,7 @@ def load(path: str | None = None) -> C.CDLL:
     L.sdrb_chain_launch_count.argtypes = [vp]
     L.sdrb_chain_launch_count.restype = C.c_longlong
     L.sdrb_chain_set_overlap.argtypes = [vp, ci]
+    L.sdrb_chain_set_stream.argtypes = [vp, vp]
     L.sdrb_pinned_alloc.argtypes = [sz, C.POINTER(vp)]
     L.sdrb_pinned_free.argtypes = [vp]
     return L
@@ -247,6 +248,9 @@ class Chain:
 
     def set_profiling(self, on: bool):
         check(self.L.sdrb_chain_set_profiling(self.h, 1 if on else 0))
+
+    def set_stream(self, cuda_stream: int):
+        check(self.L.sdrb_chain_set_stream(self.h, cuda_stream))
 
     def set_overlap(self, on: bool):
         check(self.L.sdrb_chain_set_overlap(self.h, 1 if on else 0))

@@ -74,6 +74,7 @@ struct sdrb_chain {
     long long block = 0;  // index of the next block to process
     long long launches = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = false;
     // taps
     Taps101 rf_h, pilot_h, stereo_h, rds_h, rds114_h, rrc_h, audio_h;
     float* d_audio_pm = nullptr;   // phase-major audio taps (up > 1)
@@ -150,6 +151,11 @@ int check_launch(sdrb_chain* c, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, what);
     c->launches++;
+    static const bool debug_sync = getenv("SDRB_DEBUG_SYNC") != nullptr;  // attribute an asynchronous fault to its kernel
+    if (debug_sync) {
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return cuda_fail(e, what);
+    }
     return SDRB_OK;
 }
 
@@ -344,7 +350,7 @@ int sdrb_chain_destroy(sdrb_chain* c) {
         cudaEventDestroy(t.e0);
         cudaEventDestroy(t.e1);
     }
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return SDRB_OK;
 }
@@ -406,6 +412,7 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
     } while (0)
 
     TRYCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
 
     // ---- taps (all designed on the host, same libm as the reference build)
     std::vector<float> h(kTaps);
@@ -551,6 +558,18 @@ int sdrb_chain_sync(sdrb_chain* c) {
 int sdrb_chain_set_overlap(sdrb_chain* c, int on) {
     if (!c) return fail(SDRB_ERR_INVALID, "null argument");
     c->overlap = on != 0;
+    return SDRB_OK;
+}
+
+int sdrb_chain_set_stream(sdrb_chain* c, void* stream) {
+    if (!c) return fail(SDRB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) {
+        cudaStreamDestroy(c->stream);
+        c->own_stream = false;
+    }
+    c->stream = (cudaStream_t)stream;
     return SDRB_OK;
 }
 

@@ -581,6 +581,14 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     __shared__ int8_t stype[kBitBufWords * 32];
     __shared__ int soff;
 
+    // Carried decoder state: every thread reads it here, before the first barrier; thread 0 rewrites it only
+    // after the last one (reading it later would race with that write across warps).
+    RdsStreamState* st = a.st + s;
+    RdsRecord* rec = a.rec + s;
+    const int block_count = st->block_count;
+    const int start_in = st->start, half_in = st->half_symbol, last_in = st->last_bit;
+    const int nbits_in = st->nbits, decoder_cont_in = st->decoder_cont;
+
     // ---- stage rds_dc (with the carried 100-sample state in front)
     const float* dc = a.dc + (size_t)s * a.dc_pitch - kState;
     for (int u = t; u < n_in + kState; u += kRdsThreads) sdc[u] = dc[u];
@@ -640,9 +648,6 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     }
     __syncthreads();
 
-    RdsStreamState* st = a.st + s;
-    RdsRecord* rec = a.rec + s;
-    const int block_count = st->block_count;
     const bool decode = block_count > 5 && a.rds_on;  // src/rds.cpp:135
     if (!decode) {
         if (t == 0) {
@@ -651,9 +656,6 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
         }
         return;
     }
-    // carried decoder state, read by every thread before the barriers below (lane 0 rewrites it at the end)
-    const int start_in = st->start, half_in = st->half_symbol, last_in = st->last_bit;
-    const int nbits_in = st->nbits, decoder_cont_in = st->decoder_cont;
 
     // ---- clock recovery: argmax over the sps sampling phases of sum |(int)x| (src/rds_utilities.cpp:4-21)
     const int sps = a.sps;
