@@ -163,6 +163,31 @@ constexpr double kReduceLimit = 3.0e9;  // |x| below this: k < 2^31, exact Cody-
 // rounds with relative error 2^-53; step 4 adds k*2^-122 absolute.  |r| stays >= 2^-30 for every
 // float below kReduceLimit (checked exhaustively, tests/test_pllmath.py), so r is good to ~2^-53
 // relative; the callers still send |r| < 2^-30 to the slow tier.
+// sin r and cos r for |r| <= pi/4 (+ a little), Taylor through r^17 / r^18, Estrin evaluation.
+SDRB_HD void sincos_poly(double r, double& sr, double& cr_) {
+    double z = dmul(r, r);
+    double z2 = dmul(z, z), z4 = dmul(z2, z2);
+    // sin r = r + r z (S1 + S2 z + ... + S8 z^7),  Sj = (-1)^j / (2j+1)!
+    double sa = dfma(0x1.1111111111111p-7, z, -0x1.5555555555555p-3);    //  1/120, -1/6
+    double sb = dfma(0x1.71de3a556c734p-19, z, -0x1.a01a01a01a01ap-13);  //  1/362880, -1/5040
+    double sc = dfma(0x1.6124613a86d09p-33, z, -0x1.ae64567f544e4p-26);  //  1/6227020800, -1/39916800
+    double sd = dfma(0x1.952c77030ad4ap-49, z, -0x1.ae7f3e733b81fp-41);  //  1/355687428096000, -1/1307674368000
+    double sp = dfma(dfma(sd, z2, sc), z4, dfma(sb, z2, sa));
+    sr = dfma(dmul(r, z), sp, r);
+    // cos r = 1 - z/2 + z^2 (C2 + C3 z + ... + C9 z^7),  Cj = (-1)^j / (2j)!
+    double ca = dfma(-0x1.6c16c16c16c17p-10, z, 0x1.5555555555555p-5);   // -1/720, 1/24
+    double cb = dfma(-0x1.27e4fb7789f5cp-22, z, 0x1.a01a01a01a01ap-16);  // -1/3628800, 1/40320
+    double cc = dfma(-0x1.93974a8c07c9dp-37, z, 0x1.1eed8eff8d898p-29);  // -1/87178291200, 1/479001600
+    double cd = dfma(-0x1.6827863b97d97p-53, z, 0x1.ae7f3e733b81fp-45);  // -1/6402373705728000, 1/20922789888000
+    double cp = dfma(dfma(cd, z2, cc), z4, dfma(cb, z2, ca));
+    cr_ = dfma(z2, cp, dfma(-0.5, z, 1.0));
+}
+SDRB_HD void sincos_quadrant(int q, double sr, double cr_, double& s, double& c) {
+    double ss = (q & 1) ? cr_ : sr;
+    double cs = (q & 1) ? sr : cr_;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cs : cs;
+}
 SDRB_HD void sincos_fast(double x, double& s, double& c, bool& tiny) {
     double kd = rint(dmul(x, kTwoOverPi));
     double r = dfma(-kd, kP1, x);
@@ -170,27 +195,9 @@ SDRB_HD void sincos_fast(double x, double& s, double& c, bool& tiny) {
     r = dfma(-kd, kP3, r);
     r = dfma(-kd, kP4Rest, r);
     tiny = (kd != 0.0) && fabs(r) < 0x1p-30;  // kd == 0: r = x exactly
-    double z = dmul(r, r);
-    double z2 = dmul(z, z), z4 = dmul(z2, z2);
-    // sin r = r + r z (S1 + S2 z + ... + S8 z^7),  Sj = (-1)^j / (2j+1)!   (Taylor through r^17)
-    double sa = dfma(0x1.1111111111111p-7, z, -0x1.5555555555555p-3);    //  1/120, -1/6
-    double sb = dfma(0x1.71de3a556c734p-19, z, -0x1.a01a01a01a01ap-13);  //  1/362880, -1/5040
-    double sc = dfma(0x1.6124613a86d09p-33, z, -0x1.ae64567f544e4p-26);  //  1/6227020800, -1/39916800
-    double sd = dfma(0x1.952c77030ad4ap-49, z, -0x1.ae7f3e733b81fp-41);  //  1/355687428096000, -1/1307674368000
-    double sp = dfma(dfma(sd, z2, sc), z4, dfma(sb, z2, sa));
-    double sr = dfma(dmul(r, z), sp, r);
-    // cos r = 1 - z/2 + z^2 (C2 + C3 z + ... + C9 z^7),  Cj = (-1)^j / (2j)!   (Taylor through r^18)
-    double ca = dfma(-0x1.6c16c16c16c17p-10, z, 0x1.5555555555555p-5);   // -1/720, 1/24
-    double cb = dfma(-0x1.27e4fb7789f5cp-22, z, 0x1.a01a01a01a01ap-16);  // -1/3628800, 1/40320
-    double cc = dfma(-0x1.93974a8c07c9dp-37, z, 0x1.1eed8eff8d898p-29);  // -1/87178291200, 1/479001600
-    double cd = dfma(-0x1.6827863b97d97p-53, z, 0x1.ae7f3e733b81fp-45);  // -1/6402373705728000, 1/20922789888000
-    double cp = dfma(dfma(cd, z2, cc), z4, dfma(cb, z2, ca));
-    double cr_ = dfma(z2, cp, dfma(-0.5, z, 1.0));
-    int q = (int)((long long)kd & 3);
-    double ss = (q & 1) ? cr_ : sr;
-    double cs = (q & 1) ? sr : cr_;
-    s = (q & 2) ? -ss : ss;
-    c = ((q + 1) & 2) ? -cs : cs;
+    double sr, cr_;
+    sincos_poly(r, sr, cr_);
+    sincos_quadrant((int)((long long)kd & 3), sr, cr_, s, c);
 }
 
 // slow tier: the same k, the reduction carried in double-double with pi/2 to ~170 bits, Taylor series
@@ -372,6 +379,122 @@ SDRB_HD float pll_step_trig(float in, PllState& st, const PllCoef& k, const Atan
 SDRB_HD float nco_out(float trigArg, const PllCoef& k) { return cos_f(fadd(fmul(trigArg, k.ncoScale), k.phaseAdjust)); }
 SDRB_HD float pll_step(float in, PllState& st, const PllCoef& k, const AtanTab& tab) {
     return nco_out(pll_step_trig(in, st, k, tab), k);
+}
+
+// ---- the same recurrence with a short dependency chain (what the batched kernel runs) ----
+//
+// The phase detector's inputs are errorI = RN(in*feedbackI), errorQ = RN(in*-feedbackQ) with
+// feedbackI/Q = RN_float(cos/sin(theta)) of the PREVIOUS step, so atan2(errorQ, errorI) equals
+// -theta (+pi when in < 0), wrapped to (-pi, pi], plus a perturbation delta of at most ~2^-23 rad that
+// comes from the four float roundings.  Rotating (errorI, errorQ) by +theta with the double-precision
+// cos/sin the previous step already produced gives  delta = atan(u/v),  u = errorI*sin + errorQ*cos,
+// v = errorI*cos - errorQ*sin = in*(1 + O(2^-23));  for |delta| < 2^-22, atan(u/v) = u/in up to 2^-45.
+// That replaces a table-driven atan2 with a double division by two multiplies and three adds.  The result
+// is accepted only if it is farther than kAtanAbsTol from a float rounding boundary, otherwise (and for
+// zero / subnormal / inconsistent inputs) the general correctly-rounded atan2_f above decides.
+struct PllFast {
+    float fbI, fbQ, integ, phase;  // pllblock_args fields (/root/reference/include/pll.h:10-17)
+    double trigOffset;
+    double c0, s0;  // cos/sin of the current NCO phase in double (fbI/fbQ are their float roundings)
+    double r;       // that phase reduced: theta = r + kq*pi/2 (mod 2 pi)
+    int kq;
+    bool generic_next;  // c0/s0/r/kq are not valid: use the general atan2 at the next step
+};
+constexpr double kMagicRint = 6755399441055744.0;  // 1.5 * 2^52: x + magic - magic = rint(x), integer in the low word
+constexpr int kAtanTolLog2 = -43;                  // absolute error bound of the rotated phase detector, see above
+
+// v is within 2^kAtanTolLog2 of a float rounding boundary (or too small for the bound to mean anything)
+SDRB_HD bool near_float_boundary_abs(double v) {
+    uint64_t b = dbits(v);
+    int e = (int)((b >> 52) & 0x7FFu) - 1023;
+    if (e < -17 || e > 1) return true;
+    uint32_t low = (uint32_t)b & 0x1FFFFFFFu;  // units of 2^(e-52)
+    uint32_t dist = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
+    return dist <= (1u << (52 + kAtanTolLog2 - e));
+}
+
+// quarter-turn reduction + polynomials; false if the result must not be trusted (tiny r, huge x)
+SDRB_HD bool sincos_reduced(double x, double& s, double& c, double& r_out, int& q_out) {
+    double tm = dfma(x, kTwoOverPi, kMagicRint);
+    double kd = dadd(tm, -kMagicRint);
+    int q = (int)(uint32_t)dbits(tm) & 3;
+    double r = dfma(-kd, kP2, dfma(-kd, kP1, x));       // exact: x is a float, k*P1 and k*P2 are exact
+    double tail = dfma(kd, kP3, dmul(kd, kP4Rest));
+    r = dadd(r, -tail);
+    double sr, cr_;
+    sincos_poly(r, sr, cr_);
+    sincos_quadrant(q, sr, cr_, s, c);
+    r_out = r;
+    q_out = q;
+    return !((kd != 0.0) && fabs(r) < 0x1p-30);
+}
+
+SDRB_HD void pll_fast_sincos(float trigArg, PllFast& f) {
+    double x = (double)trigArg;
+    bool ok = fabs(x) < kReduceLimit && trigArg != 0.0f;
+    if (ok) {
+        double ds, dc, r;
+        int q;
+        ok = sincos_reduced(x, ds, dc, r, q) && !near_float_boundary(ds) && !near_float_boundary(dc);
+        if (ok) {
+            f.s0 = ds;
+            f.c0 = dc;
+            f.r = r;
+            f.kq = q;
+            f.fbQ = (float)ds;
+            f.fbI = (float)dc;
+            f.generic_next = false;
+        }
+    }
+    if (!ok) {
+        sincos_f(trigArg, f.fbQ, f.fbI);
+        f.generic_next = true;
+    }
+}
+
+SDRB_HD void pll_fast_load(PllFast& f, const PllState& st, const PllCoef& k) {
+    f.integ = st.integrator;
+    f.phase = st.phaseEst;
+    f.trigOffset = st.trigOffset;
+    // the phase the carried feedbackI/Q were computed from (/root/reference/src/pll.cpp:47 with the carried values)
+    float trigArg = (float)dadd(dmul(k.w, st.trigOffset), (double)st.phaseEst);
+    pll_fast_sincos(trigArg, f);
+    // a state that did not come out of this recurrence (hand-made feedback values): keep it, go general once
+    if (f.fbI != st.feedbackI || f.fbQ != st.feedbackQ) f.generic_next = true;
+    f.fbI = st.feedbackI;
+    f.fbQ = st.feedbackQ;
+}
+SDRB_HD void pll_fast_store(const PllFast& f, PllState& st) {
+    st.feedbackI = f.fbI;
+    st.feedbackQ = f.fbQ;
+    st.integrator = f.integ;
+    st.phaseEst = f.phase;
+    st.trigOffset = f.trigOffset;
+}
+
+// One sample.  rin = 1.0 / (double)in, computed off the critical path by the caller.  Returns trigArg.
+SDRB_HD float pll_step_fast(float in, double rin, PllFast& f, const PllCoef& k, const AtanTab& tab) {
+    const float x = fmul(in, f.fbI);
+    const float y = fmul(in, -f.fbQ);
+    float errorD;
+    bool ok = !f.generic_next && x != 0.0f && y != 0.0f;
+    if (ok) {
+        double u = dfma((double)y, f.c0, dmul((double)x, f.s0));
+        double w = dmul(u, rin);
+        int m = (f.kq + (in < 0.0f ? 2 : 0)) & 3;
+        // -theta (+pi) = -r - m*pi/2, brought into (-pi, pi]:  m: 0 -> 0, 1 -> -pi/2, 3 -> +pi/2, 2 -> -+pi
+        double mm = (m == 0) ? 0.0 : (m == 1) ? -1.0 : (m == 3) ? 1.0 : (f.r > 0.0 ? 2.0 : -2.0);
+        double e = dadd(dadd(dmul(mm, kPio2H), -f.r), dfma(mm, kPio2M, w));
+        ok = fabs(w) < 0x1p-22 && fabs(e) < 3.14159 && !near_float_boundary_abs(e);
+        errorD = (float)e;
+    }
+    if (!ok) errorD = atan2_f(y, x, tab);
+    f.integ = fadd(f.integ, fmul(k.Ki, errorD));
+    f.phase = fadd(fadd(f.phase, fmul(k.Kp, errorD)), f.integ);
+    f.trigOffset = dadd(f.trigOffset, 1.0);
+    float trigArg = (float)dadd(dmul(k.w, f.trigOffset), (double)f.phase);
+    pll_fast_sincos(trigArg, f);
+    return trigArg;
 }
 
 }  // namespace cr

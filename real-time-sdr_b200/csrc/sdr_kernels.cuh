@@ -292,6 +292,14 @@ struct PllArgs {
 
 constexpr int kPllThreads = 32;
 
+// 1/(double)v to ~2^-40 relative (MUFU.RCP64H seed + one Newton step); v = 0 or subnormal gives inf/NaN, which
+// the caller's |w| test turns into the general path.  Only ~2^-25 is needed (see pll_step_fast).
+__device__ __forceinline__ double pll_recip(float v) {
+    double d = (double)v, r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    return __fma_rn(r, __fma_rn(-d, r, 1.0), r);
+}
+
 __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
     __shared__ cr::AtanTab tab;
     {
@@ -308,24 +316,34 @@ __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
     PllStateDev sd = lp.st[s];
     cr::PllState st{sd.feedbackI, sd.feedbackQ, sd.integrator, sd.phaseEst, sd.trigOffset};
     const cr::PllCoef k = lp.coef;
+    cr::PllFast f;
+    cr::pll_fast_load(f, st, k);
     const float* x = lp.x + (size_t)s * lp.x_pitch;
     float* out = lp.trig.cur + (size_t)s * lp.trig.pitch;
     const int n4 = a.n & ~3;
-    float4 nx = (n4 > 0) ? *reinterpret_cast<const float4*>(x) : make_float4(0, 0, 0, 0);
+    // Software pipeline: the loads and the reciprocals 1/in of chunk c+1 (needed by the rotated phase detector,
+    // independent of the loop state) are issued while the dependent chain of chunk c runs.
+    float4 nx = (n4 > 0) ? *reinterpret_cast<const float4*>(x) : make_float4(1.f, 1.f, 1.f, 1.f);
+    double r0 = pll_recip(nx.x), r1 = pll_recip(nx.y), r2 = pll_recip(nx.z), r3 = pll_recip(nx.w);
     for (int i = 0; i < n4; i += 4) {
-        float4 c = nx;
-        if (i + 4 < n4) nx = *reinterpret_cast<const float4*>(x + i + 4);
+        const float4 c = nx;
+        const double q0 = r0, q1 = r1, q2 = r2, q3 = r3;
+        if (i + 4 < n4) {
+            nx = *reinterpret_cast<const float4*>(x + i + 4);
+            r0 = pll_recip(nx.x); r1 = pll_recip(nx.y); r2 = pll_recip(nx.z); r3 = pll_recip(nx.w);
+        }
         float4 o;
-        o.x = cr::pll_step_trig(c.x, st, k, tab);
-        o.y = cr::pll_step_trig(c.y, st, k, tab);
-        o.z = cr::pll_step_trig(c.z, st, k, tab);
-        o.w = cr::pll_step_trig(c.w, st, k, tab);
+        o.x = cr::pll_step_fast(c.x, q0, f, k, tab);
+        o.y = cr::pll_step_fast(c.y, q1, f, k, tab);
+        o.z = cr::pll_step_fast(c.z, q2, f, k, tab);
+        o.w = cr::pll_step_fast(c.w, q3, f, k, tab);
         *reinterpret_cast<float4*>(out + i) = o;
     }
-    for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_trig(x[i], st, k, tab);
+    for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_fast(x[i], pll_recip(x[i]), f, k, tab);
     // tail -> halo of the next slot
     float* nh = lp.trig.nxt + (size_t)s * lp.trig.pitch;
     for (int b = 1; b <= lp.trig.halo && b <= a.n; b++) nh[-b] = out[a.n - b];
+    cr::pll_fast_store(f, st);
     lp.st[s] = PllStateDev{st.feedbackI, st.feedbackQ, st.integrator, st.phaseEst, st.trigOffset};
 }
 

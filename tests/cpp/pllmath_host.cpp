@@ -113,4 +113,26 @@ void crh_pll(const float* in, int n, float freq, float Fs, float scale, float ad
     for (int i = 0; i < n; i++) out[i + 1] = pll_step(in[i], st, k, kTab);
     st4[0] = st.feedbackI; st4[1] = st.feedbackQ; st4[2] = st.integrator; st4[3] = st.phaseEst; *trig = st.trigOffset;
 }
+
+// The short-chain recurrence the batched kernel runs (pll_step_fast); also returns how many steps fell back
+// to the general atan2 / sincos (stats[0], stats[1]).
+void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, float adjust, float bw, float* out,
+                  float* st4, double* trig, uint64_t* stats) {
+    PllCoef k = pll_coef(freq, Fs, scale, adjust, bw);
+    PllState st{st4[0], st4[1], st4[2], st4[3], *trig};
+    PllFast f;
+    pll_fast_load(f, st, k);
+    out[0] = out[n];
+    uint64_t gen_atan = 0, gen_sc = 0;
+    for (int i = 0; i < n; i++) {
+        float x = in[i] * f.fbI, y = in[i] * -f.fbQ;
+        if (f.generic_next || x == 0.0f || y == 0.0f) gen_atan++;
+        float th = pll_step_fast(in[i], 1.0 / (double)in[i], f, k, kTab);
+        if (f.generic_next) gen_sc++;
+        out[i + 1] = nco_out(th, k);
+    }
+    pll_fast_store(f, st);
+    st4[0] = st.feedbackI; st4[1] = st.feedbackQ; st4[2] = st.integrator; st4[3] = st.phaseEst; *trig = st.trigOffset;
+    if (stats) { stats[0] += gen_atan; stats[1] += gen_sc; }
+}
 }

@@ -101,3 +101,46 @@ def test_pll_recurrence_equals_oracle(host, oracle, station_iq, name, outn, freq
         ys.append(out.copy())
     y = np.concatenate(ys)
     assert int((y.view(np.uint32) != a[outn].view(np.uint32)).sum()) == 0
+
+
+def _run_fast(host, x, freq, scale, bw, n):
+    host.crh_pll_fast.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, f32p, f32p,
+                                  C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    out = np.zeros(n + 1, np.float32)
+    out[n] = 1
+    st = np.array([1, 0, 0, 0], np.float32)
+    trig = C.c_double(0)
+    stats = (C.c_uint64 * 2)()
+    ys = []
+    for b in range(x.size // n):
+        host.crh_pll_fast(np.ascontiguousarray(x[b * n:(b + 1) * n]), n, freq, 240000.0, scale, 0.0, bw, out, st, C.byref(trig), stats)
+        ys.append(out.copy())
+    return np.concatenate(ys), list(stats)
+
+
+@pytest.mark.parametrize("name,outn,freq,scale,bw", [("pilot", "carrier", 19e3, 2.0, 0.01), ("gen_pilot", "IPLL", 114e3, 0.5, 0.001)])
+def test_fast_recurrence_equals_oracle_on_chain_signals(host, oracle, station_iq, name, outn, freq, scale, bw):
+    """pll_step_fast (rotated phase detector, what k_pll runs) on the chain's own PLL inputs, incl. state reload per block."""
+    nblocks, n = 60, 7350
+    a = oracle.chain(0, "r", station_iq(0, 0, nblocks), stages=(name, outn))
+    y, stats = _run_fast(host, a[name], freq, scale, bw, n)
+    assert int((y.view(np.uint32) != a[outn].view(np.uint32)).sum()) == 0
+    assert stats[0] < 100 and stats[1] < 100, "the general path must stay rare on real signals"
+
+
+def test_fast_recurrence_edge_inputs(host, oracle):
+    rng = np.random.default_rng(0)
+    n, nb = 2000, 8
+    cases = {
+        "noise": (rng.standard_normal(n * nb) * 0.02).astype(np.float32),
+        "zeros": np.zeros(n * nb, np.float32),
+        "subnormal": (rng.standard_normal(n * nb) * 1e-38).astype(np.float32),
+        "huge": (rng.standard_normal(n * nb) * 1e30).astype(np.float32),
+        "sparse": np.where(rng.random(n * nb) < 0.3, 0, rng.standard_normal(n * nb)).astype(np.float32),
+        "negated_tone": (-0.05 * np.cos(2 * np.pi * 19000 / 240000 * np.arange(n * nb))).astype(np.float32),
+    }
+    for nm, x in cases.items():
+        for freq, scale, bw in ((19e3, 2.0, 0.01), (114e3, 0.5, 0.001)):
+            want, _ = oracle.pll(x, freq, 240000.0, scale, 0.0, bw, nblocks=nb)
+            y, _ = _run_fast(host, x, freq, scale, bw, n)
+            assert int((y.view(np.uint32) != want.view(np.uint32)).sum()) == 0, (nm, freq)
