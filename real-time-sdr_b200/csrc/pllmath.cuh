@@ -497,5 +497,58 @@ SDRB_HD float pll_step_fast(float in, double rin, PllFast& f, const PllCoef& k, 
     return trigArg;
 }
 
+// ---- speculative form: the same step without a single branch ----
+// Every acceptance test of pll_step_fast is a side computation OR-ed into `bad`; nothing on the recurrence
+// waits for it.  The caller runs a few steps, looks at `bad` once, and in the (rare, ~1e-5 per step) case that
+// any test failed restores the state it saved and repeats those steps with pll_step_fast.
+SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, bool& bad) {
+    const float x = fmul(in, f.fbI);
+    const float y = fmul(in, -f.fbQ);
+    const int m = (f.kq + (in < 0.0f ? 2 : 0)) & 3;
+    const double mm = (m == 0) ? 0.0 : (m == 1) ? -1.0 : (m == 3) ? 1.0 : (f.r > 0.0 ? 2.0 : -2.0);
+    const double base = dadd(dmul(mm, kPio2H), -f.r);
+    const double u = dfma((double)y, f.c0, dmul((double)x, f.s0));
+    const double w = dmul(u, rin);
+    const double e = dadd(base, dfma(mm, kPio2M, w));
+    bad = bad || x == 0.0f || y == 0.0f || !(fabs(w) < 0x1p-22) || !(fabs(e) < 3.14159) || near_float_boundary_abs(e);
+    const float errorD = (float)e;
+    f.integ = fadd(f.integ, fmul(k.Ki, errorD));
+    f.phase = fadd(fadd(f.phase, fmul(k.Kp, errorD)), f.integ);
+    f.trigOffset = dadd(f.trigOffset, 1.0);
+    const double td = dadd(dmul(k.w, f.trigOffset), (double)f.phase);
+    const float trigArg = (float)td;
+    // (double)trigArg without the float round trip: Veltkamp's split rounds td to 24 significant bits (to nearest);
+    // an exact tie could round the other way, so ties and anything outside the float-normal range count as bad.
+    const double vt = dmul(td, 536870913.0);  // 2^29 + 1
+    const double xd = dadd(vt, -dadd(vt, -td));
+    bad = bad || !(fabs(td) < kReduceLimit) || !(fabs(td) > 0x1p-100) || ((uint32_t)dbits(td) & 0x1FFFFFFFu) == 0x10000000u;
+    double ds, dc, r;
+    int q;
+    bad = !sincos_reduced(xd, ds, dc, r, q) || bad || near_float_boundary(ds) || near_float_boundary(dc);
+    f.s0 = ds;
+    f.c0 = dc;
+    f.r = r;
+    f.kq = q;
+    f.fbQ = (float)ds;
+    f.fbI = (float)dc;
+    return trigArg;
+}
+
+// N consecutive samples: speculative run, verified once; the careful path only on failure.
+template <int N>
+SDRB_HD void pll_chunk(const float (&in)[N], const double (&rin)[N], PllFast& f, const PllCoef& k, const AtanTab& tab,
+                       float (&trig)[N]) {
+    const PllFast saved = f;
+    bool bad = f.generic_next;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < N; i++) trig[i] = pll_step_spec(in[i], rin[i], f, k, bad);
+    if (bad) {
+        f = saved;
+        for (int i = 0; i < N; i++) trig[i] = pll_step_fast(in[i], rin[i], f, k, tab);
+    }
+}
+
 }  // namespace cr
 }  // namespace sdrb

@@ -124,11 +124,20 @@ void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, flo
     pll_fast_load(f, st, k);
     out[0] = out[n];
     uint64_t gen_atan = 0, gen_sc = 0;
-    for (int i = 0; i < n; i++) {
-        float x = in[i] * f.fbI, y = in[i] * -f.fbQ;
-        if (f.generic_next || x == 0.0f || y == 0.0f) gen_atan++;
-        float th = pll_step_fast(in[i], 1.0 / (double)in[i], f, k, kTab);
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {  // the kernel's chunking: 4 speculative steps, verified once
+        float c[4] = {in[i], in[i + 1], in[i + 2], in[i + 3]}, th[4];
+        double r[4] = {1.0 / (double)c[0], 1.0 / (double)c[1], 1.0 / (double)c[2], 1.0 / (double)c[3]};
+        PllFast probe = f;
+        bool bad = f.generic_next;
+        for (int j = 0; j < 4; j++) pll_step_spec(c[j], r[j], probe, k, bad);
+        if (bad) gen_atan++;  // chunks that needed the careful path
+        pll_chunk<4>(c, r, f, k, kTab, th);
         if (f.generic_next) gen_sc++;
+        for (int j = 0; j < 4; j++) out[i + j + 1] = nco_out(th[j], k);
+    }
+    for (; i < n; i++) {
+        float th = pll_step_fast(in[i], 1.0 / (double)in[i], f, k, kTab);
         out[i + 1] = nco_out(th, k);
     }
     pll_fast_store(f, st);
