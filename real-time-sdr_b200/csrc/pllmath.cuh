@@ -498,19 +498,39 @@ SDRB_HD float pll_step_fast(float in, double rin, PllFast& f, const PllCoef& k, 
 }
 
 // ---- speculative form: the same step without a single branch ----
-// Every acceptance test of pll_step_fast is a side computation OR-ed into `bad`; nothing on the recurrence
-// waits for it.  The caller runs a few steps, looks at `bad` once, and in the (rare, ~1e-5 per step) case that
-// any test failed restores the state it saved and repeats those steps with pll_step_fast.
-SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, bool& bad) {
+// Every acceptance test of pll_step_fast is a side computation OR-ed (bitwise, no short circuit) into `bad`;
+// nothing on the recurrence waits for it.  The caller runs a few steps, looks at `bad` once, and in the (rare,
+// ~1e-5 per step) case that any test failed restores the state it saved and repeats those steps with pll_step_fast.
+SDRB_HD unsigned ambig_rel(double v) {  // near_float_boundary, branch-free (also flags zero / float-subnormal)
+    const uint64_t b = dbits(v);
+    const uint32_t e = (uint32_t)(b >> 52) & 0x7FFu;
+    const uint32_t low = (uint32_t)b & 0x1FFFFFFFu;
+    const uint32_t dist = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
+    return (unsigned)(dist <= kAmbigUlps) | (unsigned)(e < 1023u - 126u + 1u);
+}
+SDRB_HD unsigned ambig_abs(double v) {  // near_float_boundary_abs, branch-free
+    const uint64_t b = dbits(v);
+    const int e = (int)((b >> 52) & 0x7FFu) - 1023;
+    const uint32_t low = (uint32_t)b & 0x1FFFFFFFu;
+    const uint32_t dist = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
+    const uint32_t thr = 1u << ((52 + kAtanTolLog2 - e) & 31);
+    return (unsigned)(e < -17) | (unsigned)(e > 1) | (unsigned)(dist <= thr);
+}
+
+SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, unsigned& bad) {
     const float x = fmul(in, f.fbI);
     const float y = fmul(in, -f.fbQ);
     const int m = (f.kq + (in < 0.0f ? 2 : 0)) & 3;
-    const double mm = (m == 0) ? 0.0 : (m == 1) ? -1.0 : (m == 3) ? 1.0 : (f.r > 0.0 ? 2.0 : -2.0);
+    // -theta (+pi) = -r - m*pi/2 in (-pi, pi]:  m: 0 -> 0, 1 -> -pi/2, 3 -> +pi/2, 2 -> -+pi (selects, no branches)
+    const double m2 = f.r > 0.0 ? 2.0 : -2.0;
+    const double m13 = (m & 2) ? 1.0 : -1.0;
+    const double mm = (m & 1) ? m13 : ((m & 2) ? m2 : 0.0);
     const double base = dadd(dmul(mm, kPio2H), -f.r);
     const double u = dfma((double)y, f.c0, dmul((double)x, f.s0));
     const double w = dmul(u, rin);
     const double e = dadd(base, dfma(mm, kPio2M, w));
-    bad = bad || x == 0.0f || y == 0.0f || !(fabs(w) < 0x1p-22) || !(fabs(e) < 3.14159) || near_float_boundary_abs(e);
+    bad |= (unsigned)(x == 0.0f) | (unsigned)(y == 0.0f) | (unsigned)!(fabs(w) < 0x1p-22) | (unsigned)!(fabs(e) < 3.14159) |
+           ambig_abs(e);
     const float errorD = (float)e;
     f.integ = fadd(f.integ, fmul(k.Ki, errorD));
     f.phase = fadd(fadd(f.phase, fmul(k.Kp, errorD)), f.integ);
@@ -521,10 +541,18 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     // an exact tie could round the other way, so ties and anything outside the float-normal range count as bad.
     const double vt = dmul(td, 536870913.0);  // 2^29 + 1
     const double xd = dadd(vt, -dadd(vt, -td));
-    bad = bad || !(fabs(td) < kReduceLimit) || !(fabs(td) > 0x1p-100) || ((uint32_t)dbits(td) & 0x1FFFFFFFu) == 0x10000000u;
-    double ds, dc, r;
-    int q;
-    bad = !sincos_reduced(xd, ds, dc, r, q) || bad || near_float_boundary(ds) || near_float_boundary(dc);
+    bad |= (unsigned)!(fabs(td) < kReduceLimit) | (unsigned)!(fabs(td) > 0x1p-100) |
+           (unsigned)(((uint32_t)dbits(td) & 0x1FFFFFFFu) == 0x10000000u);
+    // quarter-turn reduction and polynomials (sincos_reduced, inlined so that its test joins `bad`)
+    const double tm = dfma(xd, kTwoOverPi, kMagicRint);
+    const double kd = dadd(tm, -kMagicRint);
+    const int q = (int)(uint32_t)dbits(tm) & 3;
+    double r = dfma(-kd, kP2, dfma(-kd, kP1, xd));
+    r = dadd(r, -dfma(kd, kP3, dmul(kd, kP4Rest)));
+    double sr, cr_, ds, dc;
+    sincos_poly(r, sr, cr_);
+    sincos_quadrant(q, sr, cr_, ds, dc);
+    bad |= ((unsigned)(kd != 0.0) & (unsigned)(fabs(r) < 0x1p-30)) | ambig_rel(ds) | ambig_rel(dc);
     f.s0 = ds;
     f.c0 = dc;
     f.r = r;
@@ -534,19 +562,35 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     return trigArg;
 }
 
-// N consecutive samples: speculative run, verified once; the careful path only on failure.
-template <int N>
-SDRB_HD void pll_chunk(const float (&in)[N], const double (&rin)[N], PllFast& f, const PllCoef& k, const AtanTab& tab,
-                       float (&trig)[N]) {
-    const PllFast saved = f;
-    bool bad = f.generic_next;
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#define SDRB_RARE __device__ __noinline__
+#else
+#define SDRB_RARE inline
 #endif
-    for (int i = 0; i < N; i++) trig[i] = pll_step_spec(in[i], rin[i], f, k, bad);
-    if (bad) {
-        f = saved;
-        for (int i = 0; i < N; i++) trig[i] = pll_step_fast(in[i], rin[i], f, k, tab);
+// the careful repeat of four steps (rare: kept out of line on the device so the hot loop stays small)
+SDRB_RARE void pll_redo4(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, PllFast& f,
+                         const PllCoef& k, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3) {
+    t0 = pll_step_fast(i0, r0, f, k, tab);
+    t1 = pll_step_fast(i1, r1, f, k, tab);
+    t2 = pll_step_fast(i2, r2, f, k, tab);
+    t3 = pll_step_fast(i3, r3, f, k, tab);
+}
+
+// Four consecutive samples: speculative run, verified once; the careful path only on failure.
+SDRB_HD void pll_chunk4(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, PllFast& f,
+                        const PllCoef& k, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3) {
+    const PllFast saved = f;
+    unsigned bad = f.generic_next ? 1u : 0u;
+    t0 = pll_step_spec(i0, r0, f, k, bad);
+    t1 = pll_step_spec(i1, r1, f, k, bad);
+    t2 = pll_step_spec(i2, r2, f, k, bad);
+    t3 = pll_step_spec(i3, r3, f, k, bad);
+    if (bad) {  // only here does the state have to live in addressable memory (the out-of-line call)
+        PllFast again = saved;
+        float a0, a1, a2, a3;
+        pll_redo4(i0, i1, i2, i3, r0, r1, r2, r3, again, k, tab, a0, a1, a2, a3);
+        f = again;
+        t0 = a0; t1 = a1; t2 = a2; t3 = a3;
     }
 }
 

@@ -332,11 +332,8 @@ __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
             nx = *reinterpret_cast<const float4*>(x + i + 4);
             r0 = pll_recip(nx.x); r1 = pll_recip(nx.y); r2 = pll_recip(nx.z); r3 = pll_recip(nx.w);
         }
-        const float cin[4] = {c.x, c.y, c.z, c.w};
-        const double crin[4] = {q0, q1, q2, q3};
-        float th[4];
-        cr::pll_chunk<4>(cin, crin, f, k, tab, th);
-        const float4 o = make_float4(th[0], th[1], th[2], th[3]);
+        float4 o;
+        cr::pll_chunk4(c.x, c.y, c.z, c.w, q0, q1, q2, q3, f, k, tab, o.x, o.y, o.z, o.w);
         *reinterpret_cast<float4*>(out + i) = o;
     }
     for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_fast(x[i], pll_recip(x[i]), f, k, tab);

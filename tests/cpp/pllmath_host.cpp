@@ -129,10 +129,10 @@ void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, flo
         float c[4] = {in[i], in[i + 1], in[i + 2], in[i + 3]}, th[4];
         double r[4] = {1.0 / (double)c[0], 1.0 / (double)c[1], 1.0 / (double)c[2], 1.0 / (double)c[3]};
         PllFast probe = f;
-        bool bad = f.generic_next;
+        unsigned bad = f.generic_next ? 1u : 0u;
         for (int j = 0; j < 4; j++) pll_step_spec(c[j], r[j], probe, k, bad);
         if (bad) gen_atan++;  // chunks that needed the careful path
-        pll_chunk<4>(c, r, f, k, kTab, th);
+        pll_chunk4(c[0], c[1], c[2], c[3], r[0], r[1], r[2], r[3], f, k, kTab, th[0], th[1], th[2], th[3]);
         if (f.generic_next) gen_sc++;
         for (int j = 0; j < 4; j++) out[i + j + 1] = nco_out(th[j], k);
     }
