@@ -182,11 +182,21 @@ SDRB_HD void sincos_poly(double r, double& sr, double& cr_) {
     double cp = dfma(dfma(cd, z2, cc), z4, dfma(cb, z2, ca));
     cr_ = dfma(z2, cp, dfma(-0.5, z, 1.0));
 }
+SDRB_HD double flip_sign_if(double v, unsigned flip) {  // exact negation by a sign-bit XOR (one integer op on the chain)
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (int)(flip << 31), __double2loint(v));
+#else
+    uint64_t b = dbits(v) ^ ((uint64_t)flip << 63);
+    double o;
+    memcpy(&o, &b, 8);
+    return o;
+#endif
+}
 SDRB_HD void sincos_quadrant(int q, double sr, double cr_, double& s, double& c) {
     double ss = (q & 1) ? cr_ : sr;
     double cs = (q & 1) ? sr : cr_;
-    s = (q & 2) ? -ss : ss;
-    c = ((q + 1) & 2) ? -cs : cs;
+    s = flip_sign_if(ss, ((unsigned)q >> 1) & 1u);
+    c = flip_sign_if(cs, ((unsigned)(q + 1) >> 1) & 1u);
 }
 SDRB_HD void sincos_fast(double x, double& s, double& c, bool& tiny) {
     double kd = rint(dmul(x, kTwoOverPi));

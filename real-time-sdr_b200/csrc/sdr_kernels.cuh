@@ -321,20 +321,22 @@ __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
     const float* x = lp.x + (size_t)s * lp.x_pitch;
     float* out = lp.trig.cur + (size_t)s * lp.trig.pitch;
     const int n4 = a.n & ~3;
-    // Software pipeline: the loads and the reciprocals 1/in of chunk c+1 (needed by the rotated phase detector,
-    // independent of the loop state) are issued while the dependent chain of chunk c runs.
-    float4 nx = (n4 > 0) ? *reinterpret_cast<const float4*>(x) : make_float4(1.f, 1.f, 1.f, 1.f);
-    double r0 = pll_recip(nx.x), r1 = pll_recip(nx.y), r2 = pll_recip(nx.z), r3 = pll_recip(nx.w);
+    // Software pipeline, two chunks deep.  A warp issues in order, so nothing that feeds on a load may sit in
+    // the same iteration as that load: iteration c steps chunk c, computes the reciprocals 1/in of chunk c+1
+    // (loaded one iteration ago; needed by the rotated phase detector, independent of the loop state) and
+    // issues the load of chunk c+2.
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 c = (n4 > 0) ? *reinterpret_cast<const float4*>(x) : one4;
+    float4 n1 = (n4 > 4) ? *reinterpret_cast<const float4*>(x + 4) : one4;
+    double q0 = pll_recip(c.x), q1 = pll_recip(c.y), q2 = pll_recip(c.z), q3 = pll_recip(c.w);
     for (int i = 0; i < n4; i += 4) {
-        const float4 c = nx;
-        const double q0 = r0, q1 = r1, q2 = r2, q3 = r3;
-        if (i + 4 < n4) {
-            nx = *reinterpret_cast<const float4*>(x + i + 4);
-            r0 = pll_recip(nx.x); r1 = pll_recip(nx.y); r2 = pll_recip(nx.z); r3 = pll_recip(nx.w);
-        }
+        const float4 n2 = (i + 8 < n4) ? *reinterpret_cast<const float4*>(x + i + 8) : one4;
+        const double p0 = pll_recip(n1.x), p1 = pll_recip(n1.y), p2 = pll_recip(n1.z), p3 = pll_recip(n1.w);
         float4 o;
         cr::pll_chunk4(c.x, c.y, c.z, c.w, q0, q1, q2, q3, f, k, tab, o.x, o.y, o.z, o.w);
         *reinterpret_cast<float4*>(out + i) = o;
+        c = n1; n1 = n2;
+        q0 = p0; q1 = p1; q2 = p2; q3 = p3;
     }
     for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_fast(x[i], pll_recip(x[i]), f, k, tab);
     // tail -> halo of the next slot
