@@ -321,23 +321,40 @@ __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
     const float* x = lp.x + (size_t)s * lp.x_pitch;
     float* out = lp.trig.cur + (size_t)s * lp.trig.pitch;
     const int n4 = a.n & ~3;
-    // Software pipeline, two chunks deep.  A warp issues in order, so nothing that feeds on a load may sit in
-    // the same iteration as that load: iteration c steps chunk c, computes the reciprocals 1/in of chunk c+1
-    // (loaded one iteration ago; needed by the rotated phase detector, independent of the loop state) and
-    // issues the load of chunk c+2.
+    // Software pipeline, two chunks deep, unrolled three times so that the chunk registers rotate by name.
+    // A warp issues in order, so nothing that consumes a load may sit near that load: sub-iteration c steps
+    // chunk c, computes the reciprocals 1/in of chunk c+1 (loaded two sub-iterations ago; needed by the rotated
+    // phase detector, independent of the loop state) and issues the load of chunk c+2.  No register copies
+    // between iterations: a copy of a just-loaded register would stall the warp for the full load latency.
     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-    float4 c = (n4 > 0) ? *reinterpret_cast<const float4*>(x) : one4;
-    float4 n1 = (n4 > 4) ? *reinterpret_cast<const float4*>(x + 4) : one4;
-    double q0 = pll_recip(c.x), q1 = pll_recip(c.y), q2 = pll_recip(c.z), q3 = pll_recip(c.w);
-    for (int i = 0; i < n4; i += 4) {
-        const float4 n2 = (i + 8 < n4) ? *reinterpret_cast<const float4*>(x + i + 8) : one4;
-        const double p0 = pll_recip(n1.x), p1 = pll_recip(n1.y), p2 = pll_recip(n1.z), p3 = pll_recip(n1.w);
-        float4 o;
-        cr::pll_chunk4(c.x, c.y, c.z, c.w, q0, q1, q2, q3, f, k, tab, o.x, o.y, o.z, o.w);
-        *reinterpret_cast<float4*>(out + i) = o;
-        c = n1; n1 = n2;
-        q0 = p0; q1 = p1; q2 = p2; q3 = p3;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    const int nc = n4 >> 2;  // chunks
+#define SDRB_PLL_LOAD(ci) (((ci) < nc) ? x4[(ci)] : one4)
+#define SDRB_PLL_RECIP(R, V) R##0 = pll_recip(V.x); R##1 = pll_recip(V.y); R##2 = pll_recip(V.z); R##3 = pll_recip(V.w)
+#define SDRB_PLL_STEP(ci, V, R)                                                                         \
+    if ((ci) < nc) {                                                                                    \
+        float4 o;                                                                                       \
+        cr::pll_chunk4(V.x, V.y, V.z, V.w, R##0, R##1, R##2, R##3, f, k, tab, o.x, o.y, o.z, o.w);      \
+        o4[(ci)] = o;                                                                                   \
     }
+    float4 va = SDRB_PLL_LOAD(0), vb = SDRB_PLL_LOAD(1), vc;
+    double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3, rc0, rc1, rc2, rc3;
+    SDRB_PLL_RECIP(ra, va);
+    for (int ci = 0; ci < nc; ci += 3) {
+        vc = SDRB_PLL_LOAD(ci + 2);
+        SDRB_PLL_RECIP(rb, vb);
+        SDRB_PLL_STEP(ci, va, ra)
+        va = SDRB_PLL_LOAD(ci + 3);
+        SDRB_PLL_RECIP(rc, vc);
+        SDRB_PLL_STEP(ci + 1, vb, rb)
+        vb = SDRB_PLL_LOAD(ci + 4);
+        SDRB_PLL_RECIP(ra, va);
+        SDRB_PLL_STEP(ci + 2, vc, rc)
+    }
+#undef SDRB_PLL_LOAD
+#undef SDRB_PLL_RECIP
+#undef SDRB_PLL_STEP
     for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_fast(x[i], pll_recip(x[i]), f, k, tab);
     // tail -> halo of the next slot
     float* nh = lp.trig.nxt + (size_t)s * lp.trig.pitch;
