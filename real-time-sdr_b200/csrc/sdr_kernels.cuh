@@ -300,8 +300,11 @@ __device__ __forceinline__ double pll_recip(float v) {
     return __fma_rn(r, __fma_rn(-d, r, 1.0), r);
 }
 
+constexpr int kPllTileChunks = 8;  // 32 steps per staged tile
+
 __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
     __shared__ cr::AtanTab tab;
+    __shared__ __align__(16) float tile[3][kPllThreads][4 * kPllTileChunks + 4];
     {
         const cr::AtanTab init = SDRB_ATAN_TAB_INIT;
         if (threadIdx.x < 17) {
@@ -321,40 +324,54 @@ __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
     const float* x = lp.x + (size_t)s * lp.x_pitch;
     float* out = lp.trig.cur + (size_t)s * lp.trig.pitch;
     const int n4 = a.n & ~3;
-    // Software pipeline, two chunks deep, unrolled three times so that the chunk registers rotate by name.
-    // A warp issues in order, so nothing that consumes a load may sit near that load: sub-iteration c steps
-    // chunk c, computes the reciprocals 1/in of chunk c+1 (loaded two sub-iterations ago; needed by the rotated
-    // phase detector, independent of the loop state) and issues the load of chunk c+2.  No register copies
-    // between iterations: a copy of a just-loaded register would stall the warp for the full load latency.
-    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-    const float4* x4 = reinterpret_cast<const float4*>(x);
+    // Input staging: a warp issues in order, so a global load anywhere near its consumer stalls the whole
+    // recurrence for the full memory latency.  The input therefore travels through a 3-tile shared-memory ring
+    // filled with cp.async two tiles (64 steps, ~30 us) ahead; the loop only ever waits on shared memory.
+    // Row stride 36 floats keeps the per-lane LDS.128 conflict free and the 16-byte cp.async chunks aligned.
+    const int lane = threadIdx.x;
+    const int nc = n4 >> 2;                          // chunks of 4 steps
+    const int ntiles = (nc + kPllTileChunks - 1) / kPllTileChunks;
+    auto issue_tile = [&](int t) {
+        if (t < ntiles) {
+            const float* src = x + t * (4 * kPllTileChunks);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile[t % 3][lane][0]);
+#pragma unroll
+            for (int j = 0; j < kPllTileChunks; j++)
+                if (t * kPllTileChunks + j < nc)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * j), "l"(src + 4 * j) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto chunk_at = [&](int g) -> float4 {
+        return (g < nc) ? *reinterpret_cast<const float4*>(&tile[(g / kPllTileChunks) % 3][lane][4 * (g % kPllTileChunks)])
+                        : make_float4(1.f, 1.f, 1.f, 1.f);
+    };
+    issue_tile(0);
+    issue_tile(1);
+    float4 vc = make_float4(1.f, 1.f, 1.f, 1.f);
+    double q0 = 1.0, q1 = 1.0, q2 = 1.0, q3 = 1.0;
     float4* o4 = reinterpret_cast<float4*>(out);
-    const int nc = n4 >> 2;  // chunks
-#define SDRB_PLL_LOAD(ci) (((ci) < nc) ? x4[(ci)] : one4)
-#define SDRB_PLL_RECIP(R, V) R##0 = pll_recip(V.x); R##1 = pll_recip(V.y); R##2 = pll_recip(V.z); R##3 = pll_recip(V.w)
-#define SDRB_PLL_STEP(ci, V, R)                                                                         \
-    if ((ci) < nc) {                                                                                    \
-        float4 o;                                                                                       \
-        cr::pll_chunk4(V.x, V.y, V.z, V.w, R##0, R##1, R##2, R##3, f, k, tab, o.x, o.y, o.z, o.w);      \
-        o4[(ci)] = o;                                                                                   \
+    for (int g = 0; g < nc; g++) {
+        if (g % kPllTileChunks == 0) {
+            issue_tile(g / kPllTileChunks + 2);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // tiles t and t+1 have landed
+            __syncwarp();
+            if (g == 0) {
+                vc = chunk_at(0);
+                q0 = pll_recip(vc.x); q1 = pll_recip(vc.y); q2 = pll_recip(vc.z); q3 = pll_recip(vc.w);
+            }
+        }
+        // next chunk's samples and their reciprocals 1/in (needed by the rotated phase detector): independent of
+        // the loop state, they fill the issue slots the dependent chain below leaves empty
+        const float4 vn = chunk_at(g + 1);
+        const double p0 = pll_recip(vn.x), p1 = pll_recip(vn.y), p2 = pll_recip(vn.z), p3 = pll_recip(vn.w);
+        float4 o;
+        cr::pll_chunk4(vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, f, k, tab, o.x, o.y, o.z, o.w);
+        o4[g] = o;
+        vc = vn;
+        q0 = p0; q1 = p1; q2 = p2; q3 = p3;
     }
-    float4 va = SDRB_PLL_LOAD(0), vb = SDRB_PLL_LOAD(1), vc;
-    double ra0, ra1, ra2, ra3, rb0, rb1, rb2, rb3, rc0, rc1, rc2, rc3;
-    SDRB_PLL_RECIP(ra, va);
-    for (int ci = 0; ci < nc; ci += 3) {
-        vc = SDRB_PLL_LOAD(ci + 2);
-        SDRB_PLL_RECIP(rb, vb);
-        SDRB_PLL_STEP(ci, va, ra)
-        va = SDRB_PLL_LOAD(ci + 3);
-        SDRB_PLL_RECIP(rc, vc);
-        SDRB_PLL_STEP(ci + 1, vb, rb)
-        vb = SDRB_PLL_LOAD(ci + 4);
-        SDRB_PLL_RECIP(ra, va);
-        SDRB_PLL_STEP(ci + 2, vc, rc)
-    }
-#undef SDRB_PLL_LOAD
-#undef SDRB_PLL_RECIP
-#undef SDRB_PLL_STEP
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_fast(x[i], pll_recip(x[i]), f, k, tab);
     // tail -> halo of the next slot
     float* nh = lp.trig.nxt + (size_t)s * lp.trig.pitch;
