@@ -1,0 +1,3 @@
+// Same name as the reference header include/filter.h: code written against the reference compiles unchanged.
+#pragma once
+#include "../dy4_api.h"

@@ -1,0 +1,249 @@
+// Implementation of dy4_api.h on the C ABI of libsdr_b200 (see the header for the contract).
+#include "dy4_api.h"
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+
+#include "../../include/sdr_b200.h"
+
+namespace {
+
+void ok(int rc) {
+    if (rc != SDRB_OK) throw std::runtime_error(std::string("libsdr_b200: ") + sdrb_last_error());
+}
+void cu(cudaError_t e) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e));
+}
+
+// device buffer holding a copy of a host vector (batch = 1 staging for the single-stream API)
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    explicit DevBuf(size_t count) : n(count) { cu(cudaMalloc((void**)&p, sizeof(T) * (count ? count : 1))); }
+    DevBuf(const T* src, size_t count) : DevBuf(count) { if (count) cu(cudaMemcpy(p, src, sizeof(T) * count, cudaMemcpyHostToDevice)); }
+    ~DevBuf() { cudaFree(p); }
+    void to_host(T* dst, size_t count) const { if (count) cu(cudaMemcpy(dst, p, sizeof(T) * count, cudaMemcpyDeviceToHost)); }
+};
+
+// RDS block check (src/rds_utilities.cpp:122-135): parity rows and syndromes as 26-/10-bit masks, first received
+// bit = bit 0.  Same constants as the device kernel (sdr_kernels.cuh: rds_block_type).
+const uint32_t kParityRows[10] = {0x39BE401u, 0x337C802u, 0x1F47404u, 0x0730C08u, 0x0E61810u,
+                                  0x257D420u, 0x3344C40u, 0x1F37C80u, 0x3E6F900u, 0x3CDF200u};
+const uint32_t kSyndromes[5] = {0x06Fu, 0x0AFu, 0x0E9u, 0x0CFu, 0x069u};
+const char* const kOffsetNames[5] = {"A", "B", "C", "Cp", "D"};
+
+}  // namespace
+
+// ---- tap designers: host side of the library --------------------------------------------------------------
+void impulseResponseLPF(float Fs, float Fc, unsigned short int num_taps, std::vector<float>& h) {
+    h.clear(); h.resize(num_taps, 0.0f);
+    ok(sdrb_design_lpf(Fs, Fc, num_taps, h.data()));
+}
+void impulseResponseLPF(float Fs, float Fc, unsigned short int num_taps, std::vector<float>& h, int u) {
+    h.clear(); h.resize(num_taps, 0.0f);
+    ok(sdrb_design_lpf_gain(Fs, Fc, num_taps, u, h.data()));
+}
+void impulseResponseBPF(float Fs, float* Fb, unsigned short int num_taps, std::vector<float>& h) {
+    h.clear(); h.resize(num_taps, 0.0f);
+    ok(sdrb_design_bpf(Fs, Fb[0], Fb[1], num_taps, h.data()));
+}
+void impulseResponseAPF(float gain, unsigned short int num_taps, std::vector<float>& h) {
+    h.clear(); h.resize(num_taps, 0.0f);
+    ok(sdrb_design_apf(gain, num_taps, h.data()));
+}
+void impulseResponseRRC(float Fs, unsigned short int num_taps, std::vector<float>& h) {
+    h.clear(); h.resize(num_taps, 0.0f);
+    ok(sdrb_design_rrc(Fs, num_taps, h.data()));
+}
+
+// ---- block FIRs ------------------------------------------------------------------------------------------
+void convolveFIR(std::vector<float>& y, const std::vector<float>& x, const std::vector<float>& h, std::vector<float>& state, int decim) {
+    if (h.empty() || decim < 1) throw std::invalid_argument("convolveFIR: empty taps or decim < 1");
+    if (state.size() != h.size() - 1) throw std::invalid_argument("convolveFIR: state must hold h.size()-1 samples");
+    if (x.size() < state.size()) throw std::invalid_argument("convolveFIR: x shorter than the carried state (undefined in the reference)");
+    y.clear(); y.resize(x.size() / decim, 0.0f);
+    DevBuf<float> dx(x.data(), x.size()), ds(state.data(), state.size()), dy(y.size());
+    ok(sdrb_fir_decim(dx.p, x.size(), (int)x.size(), h.data(), (int)h.size(), ds.p, dy.p, y.size() ? y.size() : 1, decim, 1, nullptr));
+    cu(cudaDeviceSynchronize());
+    dy.to_host(y.data(), y.size());
+    ds.to_host(state.data(), state.size());
+}
+
+void convolveFIR(std::vector<float>& y, const std::vector<float>& x, const std::vector<float>& h, std::vector<float>& state, int up, int down) {
+    if (h.empty() || up < 1 || down < 1) throw std::invalid_argument("convolveFIR: bad resampling ratio");
+    // The reference sizes this state like the decimator's (h.size()-1) although only the last (h.size()-1)/up entries are
+    // ever read (src/filter.cpp:135) and copies "the last h.size()-1 samples of x" even when x is shorter (:145, an
+    // out-of-bounds read).  Here: the live part is carried exactly, the never-read part is zero.
+    const size_t live = (h.size() - 1) / (size_t)up;
+    if (state.size() < live) throw std::invalid_argument("convolveFIR: state shorter than (h.size()-1)/up");
+    if (x.size() < live) throw std::invalid_argument("convolveFIR: x shorter than the live state");
+    const size_t ny = (x.size() * (size_t)up) / (size_t)down;
+    y.clear(); y.resize(ny, 0.0f);
+    std::vector<float> tail(state.end() - live, state.end());
+    DevBuf<float> dx(x.data(), x.size()), ds(tail.data(), live), dy(ny);
+    ok(sdrb_fir_updown(dx.p, x.size(), (int)x.size(), h.data(), (int)h.size(), ds.p, (int)live, dy.p, ny ? ny : 1, up, down, 1, nullptr));
+    cu(cudaDeviceSynchronize());
+    dy.to_host(y.data(), ny);
+    ds.to_host(tail.data(), live);
+    std::fill(state.begin(), state.end(), 0.0f);
+    std::copy(tail.begin(), tail.end(), state.end() - live);
+    if (x.size() >= state.size()) std::copy(x.end() - state.size(), x.end(), state.begin());  // what the reference holds when in bounds
+}
+
+// ---- discriminator ------------------------------------------------------------------------------------------
+void fmDemodNoArctan(const std::vector<float>& I, const std::vector<float>& Q, float& prev_I, float& prev_Q, std::vector<float>& fm_demod) {
+    if (I.size() != Q.size() || I.empty()) throw std::invalid_argument("fmDemodNoArctan: I and Q must be non-empty and of equal size");
+    fm_demod.clear(); fm_demod.resize(I.size());
+    float prev[2] = {prev_I, prev_Q};
+    DevBuf<float> di(I.data(), I.size()), dq(Q.data(), Q.size()), dp(prev, 2), dout(I.size());
+    ok(sdrb_fm_demod(di.p, dq.p, I.size(), (int)I.size(), dp.p, dout.p, I.size(), 1, nullptr));
+    cu(cudaDeviceSynchronize());
+    dout.to_host(fm_demod.data(), I.size());
+    dp.to_host(prev, 2);
+    prev_I = prev[0];
+    prev_Q = prev[1];
+}
+
+// ---- PLL ----------------------------------------------------------------------------------------------------
+void fmpll(const std::vector<float>& pllIn, float freq, float Fs, std::vector<float>& pllOut, pllblock_args& block, float ncoScale,
+           float phaseAdjust, float normBandwidth) {
+    const size_t n = pllIn.size();
+    if (pllOut.size() < n + 1) throw std::invalid_argument("fmpll: pllOut must be pre-sized to pllIn.size()+1 (it carries the last NCO sample)");
+    sdrb_pll_state st{block.feedbackI, block.feedbackQ, block.integrator, block.phaseEst, block.trigOffset, block.lastCarrier,
+                      pllOut[pllOut.size() - 1]};  // src/pll.cpp:18
+    DevBuf<float> din(pllIn.data(), n), dout(n + 1);
+    DevBuf<sdrb_pll_state> dst(&st, 1);
+    ok(sdrb_pll(din.p, n ? n : 1, (int)n, freq, Fs, ncoScale, phaseAdjust, normBandwidth, dst.p, dout.p, n + 1, 1, nullptr));
+    cu(cudaDeviceSynchronize());
+    dout.to_host(pllOut.data(), n + 1);
+    dst.to_host(&st, 1);
+    block.feedbackI = st.feedbackI; block.feedbackQ = st.feedbackQ; block.integrator = st.integrator;
+    block.phaseEst = st.phaseEst; block.trigOffset = st.trigOffset; block.lastCarrier = st.lastCarrier;
+}
+
+// ---- RDS symbol and bit utilities ---------------------------------------------------------------------------
+int cdr(int sps, const std::vector<float>& signal) {
+    if (sps < 1) throw std::invalid_argument("cdr: sps < 1");
+    DevBuf<float> dx(signal.data(), signal.size());
+    DevBuf<int> doff(1);
+    ok(sdrb_cdr(dx.p, signal.size() ? signal.size() : 1, (int)signal.size(), sps, doff.p, 1, nullptr));
+    cu(cudaDeviceSynchronize());
+    int off = 0;
+    doff.to_host(&off, 1);
+    return off;
+}
+
+// The three functions below work on a few dozen ints per call.  Their batched form runs on the GPU inside
+// k_rds_backend (ballots for the Manchester pairing, one shifted XOR for the differential decode, 26-bit popcount
+// syndromes for the block check); the std::vector forms exist for API compatibility and stay on the host.
+void manchester_decode(std::vector<int>& bits, const std::vector<int>& symbols, int& block_count, int& half_symbol, int& start) {
+    bits.clear();
+    const int n = (int)symbols.size();
+    if (start) bits.push_back(half_symbol);
+    if (block_count == 0) {  // pairing-phase estimate; unreachable from rds() (src/rds.cpp:135) but part of the function
+        int agree = 0;
+        for (int i = 0; i + 1 < n; i += 2) agree += symbols[i] ^ symbols[i + 1];
+        for (int i = 1; i + 1 < n; i += 2) agree -= symbols[i] ^ symbols[i + 1];
+        start = agree < 0 ? 1 : 0;
+    }
+    for (int i = start; i < n - 1; i += 2) bits.push_back(symbols[i]);
+    if (((unsigned)n - (unsigned)start) & 1u) {
+        half_symbol = symbols[n - 1];
+        start = 1;
+    } else {
+        start = 0;
+    }
+}
+
+void differential_decode(std::vector<int>& decoded, const std::vector<int>& bits, int& last_bit, int& block_num) {
+    if (bits.empty()) throw std::invalid_argument("differential_decode: empty input (undefined in the reference)");
+    decoded.assign(bits.size(), 0);
+    decoded[0] = block_num == 0 ? bits[0] : (bits[0] ^ last_bit);
+    for (size_t i = 1; i < bits.size(); i++) decoded[i] = bits[i] ^ bits[i - 1];
+    last_bit = bits.back();
+}
+
+void parse(uint64_t bytes, uint64_t& chars, uint64_t& output, bool& first_time) {
+    char text[256];
+    sdrb_rds_parse(bytes, &chars, &output, text, sizeof text);
+    std::cerr << text;
+    (void)first_time;  // the reference writes it after the first group and never reads it again
+}
+
+void check_block(std::string& offset_type, std::vector<int>::iterator b, std::vector<int>::iterator e, uint64_t& reg, uint64_t& chars,
+                 uint64_t& output, bool& first_time, std::deque<std::string>& window) {
+    uint32_t w = 0;
+    int n = 0;
+    for (auto it = b; it != e && n < 26; ++it, ++n) w |= (uint32_t)(*it != 0) << n;
+    uint32_t syn = 0;
+    for (int c = 0; c < 10; c++) syn |= (uint32_t)(__builtin_popcount(w & kParityRows[c]) & 1) << c;
+    for (int t = 0; t < 5; t++) {
+        if (syn != kSyndromes[t]) continue;
+        offset_type = kOffsetNames[t];
+        if (t != 3) {  // C' matches but carries no copy in the reference (:370)
+            const int slot = t == 4 ? 3 : t;
+            uint64_t word = 0;
+            for (int i = 0; i < 16; i++) word |= (uint64_t)((w >> i) & 1u) << (15 - i);
+            const int sh = 48 - 16 * slot;
+            reg = (reg & ~((uint64_t)0xFFFF << sh)) | (word << sh);
+        }
+        window.push_back(offset_type);
+        if (window.size() > 4) window.pop_front();
+        if (window.size() == 4 && window[0] == "A" && window[1] == "B" && window[2] == "C" && window[3] == "D") {
+            parse(reg, chars, output, first_time);
+            first_time = false;
+        }
+        return;
+    }
+    offset_type = "None";
+}
+
+void start_frame_sync(unsigned int& idx, std::vector<int>& stream, std::vector<int>& carry, uint64_t& reg, uint64_t& chars, uint64_t& output,
+                      bool& first_time, std::deque<std::string>& window) {
+    stream.insert(stream.begin(), carry.begin(), carry.end());
+    const unsigned int end_range = (unsigned int)stream.size() - 26u;  // unsigned like the reference: < 26 bits scans nothing sensible there
+    std::string kind;
+    if (stream.size() >= 26)
+        while (idx < end_range) {
+            check_block(kind, stream.begin() + idx, stream.begin() + idx + 26, reg, chars, output, first_time, window);
+            idx += kind != "None" ? 26 : 1;
+        }
+    carry.assign(stream.begin() + std::min<size_t>(idx, stream.size()), stream.end());
+}
+
+// ---- batched chain ------------------------------------------------------------------------------------------
+namespace dy4 {
+
+ReceiveChain::ReceiveChain(int mode, char type, int n_streams, int device) : n_(n_streams), rds_(type == 'r') {
+    sdrb_config cfg;
+    ok(sdrb_config_for_mode(mode, type, n_streams, &cfg));
+    cfg.device = device;
+    ok(sdrb_chain_create(&cfg, &c_));
+    chars_.assign(n_, 0);
+    output_.assign(n_, 0);
+    text_.assign(n_, std::string());
+}
+ReceiveChain::~ReceiveChain() { sdrb_chain_destroy(c_); }
+int ReceiveChain::block_bytes() const { sdrb_chain_info i; sdrb_chain_get_info(c_, &i); return i.block_bytes; }
+int ReceiveChain::pcm_per_block() const { sdrb_chain_info i; sdrb_chain_get_info(c_, &i); return i.pcm_per_block; }
+void ReceiveChain::process(const uint8_t* iq, size_t pitch) { ok(sdrb_chain_process_host(c_, iq, pitch)); }
+void ReceiveChain::read_pcm(int16_t* pcm, size_t pitch_samples) { ok(sdrb_chain_read_pcm(c_, pcm, pitch_samples)); }
+const std::vector<std::string>& ReceiveChain::rds_text() {
+    for (auto& t : text_) t.clear();
+    if (!rds_) return text_;
+    std::vector<sdrb_rds_record> rec(n_);
+    ok(sdrb_chain_read_rds(c_, rec.data()));
+    char buf[256];
+    for (int s = 0; s < n_; s++)
+        for (int g = 0; g < rec[s].n_groups; g++) {
+            sdrb_rds_parse(rec[s].groups[g], &chars_[s], &output_[s], buf, sizeof buf);
+            text_[s] += buf;
+        }
+    return text_;
+}
+
+}  // namespace dy4
