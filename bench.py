@@ -238,6 +238,7 @@ def main():
 
     # ---- device-resident throughput
     run_steps(args.warmup, 0)
+    ch.join()
     barrier()
     launches0 = ch.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -245,6 +246,7 @@ def main():
     t0 = time.perf_counter()
     e0.record(stream)
     run_steps(args.steps, args.warmup)
+    ch.join()  # the launching stream waits for the internal streams: e1 closes the whole region
     e1.record(stream)
     barrier()
     t1 = time.perf_counter()
@@ -310,16 +312,22 @@ def main():
         pcm = capi.PinnedBuffer(S * ch.info.pcm_per_block * 2)
         pcm_v = pcm.array.view(np.int16).reshape(S, ch.info.pcm_per_block)
         k_e2e = max(4, min(args.steps, 24))
-        for i in range(3):
-            ch.process_host_ptr(hv[i % n_host].ctypes.data, pitch)
-            ch.read_pcm(pcm_v)
-            ch.read_rds()
+        rec = np.zeros(S, capi.RDS_RECORD_DTYPE)
+
+        def e2e_steps(n):
+            # software pipeline of depth 1 over the public calls: block i is issued, then the results of block i-1 are
+            # read (lag 1) while block i is in flight; the last block's results are read with lag 0.
+            ch.process_host_ptr(hv[0].ctypes.data, pitch)
+            for i in range(1, n):
+                ch.process_host_ptr(hv[i % n_host].ctypes.data, pitch)
+                ch.read_results(1, pcm_v, rec)
+            ch.read_results(0, pcm_v, rec)
+
+        e2e_steps(3)
         barrier()
         t0e = time.perf_counter()
-        for i in range(k_e2e):
-            ch.process_host_ptr(hv[i % n_host].ctypes.data, pitch)
-            ch.read_pcm(pcm_v)
-            rec = ch.read_rds()
+        e2e_steps(k_e2e)
+        ch.sync()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0e
         if world > 1:
@@ -328,7 +336,7 @@ def main():
             dt = float(t.item())
         e2e = {"value": round(world * S * bp * k_e2e / dt / 1e6, 1), "unit": UNIT, "h2d_bytes_per_step": S * bb,
                "d2h_bytes_per_step": S * (ch.info.pcm_per_block * 2 + rec.dtype.itemsize), "steps": k_e2e,
-               "call": "sdrb_chain_process_host + sdrb_chain_read_pcm + sdrb_chain_read_rds (pinned host buffers)"}
+               "call": "sdrb_chain_process_host + sdrb_chain_read_results (PCM + RDS records of every block, pinned host buffers)"}
         pinned.free()
         pcm.free()
 

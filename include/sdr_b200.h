@@ -133,10 +133,16 @@ int sdrb_chain_process_host(sdrb_chain* c, const uint8_t* h_iq, size_t iq_pitch)
 
 int sdrb_chain_sync(sdrb_chain* c);
 
-/* 1 (default): the front end of block b+1 (RF front-end, band filters) may run concurrently with the PLL
- * and back end of block b on separate CUDA streams (the rings are three slots deep for this).
- * 0: every kernel of a block is issued on one stream, in order. */
+/* Overlap mode (default 0).
+ * 0: every kernel of a block is issued on the chain's stream, in order.
+ * 1: the front end of block b+1 (RF front end, band filters) runs concurrently with the PLL and back end of block b
+ *    on internal CUDA streams chained by events (the rings are three slots deep for this), and process_host copies on
+ *    a copy-engine stream.  The input buffer of a block is then read asynchronously with respect to the chain's
+ *    stream: keep it unchanged until sdrb_chain_join / _sync / a read call, or until two more blocks were issued. */
 int sdrb_chain_set_overlap(sdrb_chain* c, int on);
+
+/* Makes the chain's stream wait (on the device, without blocking the host) for everything issued so far. */
+int sdrb_chain_join(sdrb_chain* c);
 
 /* Issue this chain's work on the caller's CUDA stream (e.g. the application's or torch's current stream)
  * instead of the private stream created by sdrb_chain_create.  Call between blocks only. */
@@ -162,6 +168,10 @@ typedef struct {
     uint64_t groups[8];  /* 64-bit group registers A|B|C|D as handed to parse() (src/rds_utilities.cpp:172) */
 } sdrb_rds_record;
 int sdrb_chain_read_rds(sdrb_chain* c, sdrb_rds_record* h_records /* [n_streams] */);
+
+/* PCM and/or RDS records (either pointer may be NULL) of block (most recent - lag), lag = 0 or 1.  Outputs are double
+ * buffered by block parity, so with lag = 1 the read of block b-1 overlaps the processing of block b (overlap mode). */
+int sdrb_chain_read_results(sdrb_chain* c, int lag, int16_t* h_pcm, size_t pcm_pitch, sdrb_rds_record* h_records);
 
 /* parse() — src/rds_utilities.cpp:172-199: the text the reference prints on stderr for one group.
  * chars/output are the caller-held PS assembly state (src/rds.cpp:68-69).  Returns bytes written. */

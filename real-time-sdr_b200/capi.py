@@ -25,7 +25,7 @@ EXPORTS = [
     "sdrb_chain_pcm_device", "sdrb_chain_read_rds", "sdrb_rds_parse", "sdrb_chain_stage",
     "sdrb_chain_state_bytes", "sdrb_chain_state_save", "sdrb_chain_state_load", "sdrb_chain_kernel_times",
     "sdrb_chain_set_profiling", "sdrb_chain_launch_count", "sdrb_chain_set_overlap", "sdrb_pinned_alloc",
-    "sdrb_pinned_free", "sdrb_chain_set_stream",
+    "sdrb_pinned_free", "sdrb_chain_set_stream", "sdrb_chain_join", "sdrb_chain_read_results",
 ]
 
 
@@ -109,6 +109,8 @@ def load(path: str | None = None) -> C.CDLL:
     L.sdrb_chain_launch_count.restype = C.c_longlong
     L.sdrb_chain_set_overlap.argtypes = [vp, ci]
     L.sdrb_chain_set_stream.argtypes = [vp, vp]
+    L.sdrb_chain_join.argtypes = [vp]
+    L.sdrb_chain_read_results.argtypes = [vp, ci, vp, sz, vp]
     L.sdrb_pinned_alloc.argtypes = [sz, C.POINTER(vp)]
     L.sdrb_pinned_free.argtypes = [vp]
     return L
@@ -218,6 +220,14 @@ class Chain:
 
     def sync(self):
         check(self.L.sdrb_chain_sync(self.h))
+
+    def join(self):
+        check(self.L.sdrb_chain_join(self.h))
+
+    def read_results(self, lag: int, pcm: np.ndarray | None, rec: np.ndarray | None):
+        check(self.L.sdrb_chain_read_results(self.h, lag, pcm.ctypes.data if pcm is not None else None,
+                                             (pcm.strides[0] // 2) if pcm is not None else 0,
+                                             rec.ctypes.data if rec is not None else None))
 
     def read_pcm(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:

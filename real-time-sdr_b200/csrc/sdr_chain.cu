@@ -73,8 +73,12 @@ struct sdrb_chain {
     bool stereo = false, rds = false;
     long long block = 0;  // index of the next block to process
     long long launches = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;  // the caller-visible stream: inputs are ordered on it, joins land on it
     bool own_stream = false;
+    // overlap mode: front end of block b+1 concurrent with PLL / back end of block b (see process_block)
+    cudaStream_t s_front = nullptr, s_pll = nullptr, s_back = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_front[kNRing] = {}, ev_pll[kNRing] = {}, ev_back[kNRing] = {}, ev_h2d[2] = {}, ev_join = nullptr;
+    bool pending = false;  // work issued on the internal streams that the main stream has not been joined with
     // taps
     Taps101 rf_h, pilot_h, stereo_h, rds_h, rds114_h, rrc_h, audio_h;
     float* d_audio_pm = nullptr;   // phase-major audio taps (up > 1)
@@ -89,9 +93,9 @@ struct sdrb_chain {
     PllStateDev* d_pll[2] = {nullptr, nullptr};
     float* d_filt_state[2] = {nullptr, nullptr};
     RdsStreamState* d_rds_state = nullptr;
-    RdsRecord* d_rec = nullptr;
-    // outputs
-    int16_t* d_pcm = nullptr;
+    RdsRecord* d_rec[2] = {nullptr, nullptr};
+    // outputs, double buffered by block parity (a lagged read of block b-1 may overlap block b)
+    int16_t* d_pcm[2] = {nullptr, nullptr};
     size_t pcm_pitch = 0;
     // optional stage dumps
     float *d_ids = nullptr, *d_qds = nullptr, *d_carrier = nullptr, *d_ipll = nullptr, *d_rdelay = nullptr,
@@ -134,53 +138,84 @@ Timed* timer_for(sdrb_chain* c, const char* name) {
 
 struct ScopedTimer {
     sdrb_chain* c;
+    cudaStream_t st;
     Timed* t = nullptr;
-    ScopedTimer(sdrb_chain* c_, const char* name) : c(c_) {
+    ScopedTimer(sdrb_chain* c_, const char* name, cudaStream_t st_) : c(c_), st(st_) {
         if (c->profiling) {
             t = timer_for(c, name);
             t->used = true;
-            cudaEventRecord(t->e0, c->stream);
+            cudaEventRecord(t->e0, st);
         }
     }
     ~ScopedTimer() {
-        if (t) cudaEventRecord(t->e1, c->stream);
+        if (t) cudaEventRecord(t->e1, st);
     }
 };
 
-int check_launch(sdrb_chain* c, const char* what) {
+int check_launch(sdrb_chain* c, const char* what, cudaStream_t st) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, what);
     c->launches++;
     static const bool debug_sync = getenv("SDRB_DEBUG_SYNC") != nullptr;  // attribute an asynchronous fault to its kernel
     if (debug_sync) {
-        e = cudaStreamSynchronize(c->stream);
+        e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return cuda_fail(e, what);
     }
     return SDRB_OK;
 }
 
 template <int DECIM>
-int launch_rf(sdrb_chain* c, const RfArgs& a) {
+int launch_rf(sdrb_chain* c, const RfArgs& a, cudaStream_t st) {
     dim3 grid((c->info.if_block + kRfTile - 2) / (kRfTile - 1), c->S);
-    k_rf_frontend<DECIM><<<grid, kRfThreads, 0, c->stream>>>(c->rf_h, a);
-    return check_launch(c, "k_rf_frontend");
+    k_rf_frontend<DECIM><<<grid, kRfThreads, 0, st>>>(c->rf_h, a);
+    return check_launch(c, "k_rf_frontend", st);
 }
 
 template <int DOWN>
-int launch_audio_decim(sdrb_chain* c, const AudioArgs& a) {
+int launch_audio_decim(sdrb_chain* c, const AudioArgs& a, cudaStream_t st) {
     dim3 grid((a.n_out + kAudTile - 1) / kAudTile, c->S);
-    if (c->stereo) k_audio_decim<DOWN, true><<<grid, kAudThreads, 0, c->stream>>>(c->audio_h, a);
-    else k_audio_decim<DOWN, false><<<grid, kAudThreads, 0, c->stream>>>(c->audio_h, a);
-    return check_launch(c, "k_audio_decim");
+    if (c->stereo) k_audio_decim<DOWN, true><<<grid, kAudThreads, 0, st>>>(c->audio_h, a);
+    else k_audio_decim<DOWN, false><<<grid, kAudThreads, 0, st>>>(c->audio_h, a);
+    return check_launch(c, "k_audio_decim", st);
 }
 
-int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch) {
+// Makes the caller-visible stream wait for everything issued on the internal streams (no host blocking).
+int join_main(sdrb_chain* c) {
+    if (!c->pending) return SDRB_OK;
+    for (cudaStream_t st : {c->s_front, c->s_pll, c->s_back, c->s_h2d, c->s_d2h}) {
+        CU(cudaEventRecord(c->ev_join, st));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    }
+    c->pending = false;
+    return SDRB_OK;
+}
+
+// One block.  In overlap mode the three phases run on three streams chained by events:
+//   front(b) = RF front end + band filters   waits: input (ev_in or the H2D copy), back(b-2)  [ring slots, see sdr_kernels.cuh]
+//   pll(b)                                    waits: front(b)          (and pll(b-1): same stream)
+//   back(b)  = mixers + audio + RDS           waits: pll(b)            (and back(b-1): same stream)
+// so the FIR-heavy front end of block b+1 fills the machine while the latency-bound PLL of block b runs on a few SMs.
+int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent_t input_ready) {
     const long long b = c->block;
     const int S = c->S, n_if = c->info.if_block;
     const bool keep = c->cfg.keep_stages != 0;
+    const bool ov = c->overlap;
+    const cudaStream_t sf = ov ? c->s_front : c->stream, sp = ov ? c->s_pll : c->stream, sb = ov ? c->s_back : c->stream;
     int rc;
+    if (ov) {
+        if (input_ready) {
+            CU(cudaStreamWaitEvent(sf, input_ready, 0));
+        } else {
+            CU(cudaEventRecord(c->ev_in, c->stream));
+            CU(cudaStreamWaitEvent(sf, c->ev_in, 0));
+        }
+        if (b >= 2) CU(cudaStreamWaitEvent(sf, c->ev_back[(b - 2) % kNRing], 0));
+        c->pending = true;
+    } else if (input_ready) {
+        CU(cudaStreamWaitEvent(sf, input_ready, 0));
+    }
     {
-        ScopedTimer tm(c, "rf_frontend");
+        ScopedTimer tm(c, "rf_frontend", sf);
         RfArgs a{};
         a.iq = d_iq;
         a.iq_pitch = iq_pitch;
@@ -192,9 +227,9 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch) {
         a.i_ds = keep ? c->d_ids : nullptr;
         a.q_ds = keep ? c->d_qds : nullptr;
         switch (c->cfg.rf_decim) {
-            case 10: rc = launch_rf<10>(c, a); break;
-            case 4: rc = launch_rf<4>(c, a); break;
-            case 3: rc = launch_rf<3>(c, a); break;
+            case 10: rc = launch_rf<10>(c, a, sf); break;
+            case 4: rc = launch_rf<4>(c, a, sf); break;
+            case 3: rc = launch_rf<3>(c, a, sf); break;
             default: return fail(SDRB_ERR_INVALID, "rf_decim must be 10, 4 or 3");
         }
         if (rc) return rc;
@@ -202,33 +237,37 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch) {
     const int tiles = (n_if + kBankTile - 1) / kBankTile;
     const int bank_blocks = (int)(((long long)S * tiles + kBankWarps - 1) / kBankWarps);
     if (c->stereo && c->rds) {
-        ScopedTimer tm(c, "if_bands");
+        ScopedTimer tm(c, "if_bands", sf);
         BankArgs<3> a{};
         a.x = c->fm.cur(b); a.x_pitch = c->fm.pitch; a.n = n_if; a.tiles = tiles; a.n_streams = S;
         a.y[0] = c->pilot.view(b); a.y[1] = c->sband.view(b); a.y[2] = c->rband.view(b);
         a.taps[0] = c->pilot_h; a.taps[1] = c->stereo_h; a.taps[2] = c->rds_h;
-        k_fir_bank<3, false><<<bank_blocks, 32 * kBankWarps, 0, c->stream>>>(a);
-        if ((rc = check_launch(c, "k_fir_bank<3>"))) return rc;
+        k_fir_bank<3, false><<<bank_blocks, 32 * kBankWarps, 0, sf>>>(a);
+        if ((rc = check_launch(c, "k_fir_bank<3>", sf))) return rc;
     } else if (c->stereo) {
-        ScopedTimer tm(c, "if_bands");
+        ScopedTimer tm(c, "if_bands", sf);
         BankArgs<2> a{};
         a.x = c->fm.cur(b); a.x_pitch = c->fm.pitch; a.n = n_if; a.tiles = tiles; a.n_streams = S;
         a.y[0] = c->pilot.view(b); a.y[1] = c->sband.view(b);
         a.taps[0] = c->pilot_h; a.taps[1] = c->stereo_h;
-        k_fir_bank<2, false><<<bank_blocks, 32 * kBankWarps, 0, c->stream>>>(a);
-        if ((rc = check_launch(c, "k_fir_bank<2>"))) return rc;
+        k_fir_bank<2, false><<<bank_blocks, 32 * kBankWarps, 0, sf>>>(a);
+        if ((rc = check_launch(c, "k_fir_bank<2>", sf))) return rc;
     }
     if (c->rds) {
-        ScopedTimer tm(c, "rds_carrier_bpf");
+        ScopedTimer tm(c, "rds_carrier_bpf", sf);
         BankArgs<1> a{};
         a.x = c->rband.cur(b); a.x_pitch = c->rband.pitch; a.n = n_if; a.tiles = tiles; a.n_streams = S;
         a.y[0] = c->gpilot.view(b);
         a.taps[0] = c->rds114_h;
-        k_fir_bank<1, true><<<bank_blocks, 32 * kBankWarps, 0, c->stream>>>(a);
-        if ((rc = check_launch(c, "k_fir_bank<1,sq>"))) return rc;
+        k_fir_bank<1, true><<<bank_blocks, 32 * kBankWarps, 0, sf>>>(a);
+        if ((rc = check_launch(c, "k_fir_bank<1,sq>", sf))) return rc;
+    }
+    if (ov) {
+        CU(cudaEventRecord(c->ev_front[b % kNRing], sf));
+        CU(cudaStreamWaitEvent(sp, c->ev_front[b % kNRing], 0));
     }
     if (c->stereo) {
-        ScopedTimer tm(c, "pll");
+        ScopedTimer tm(c, "pll", sp);
         PllArgs a{};
         a.n = n_if; a.n_streams = S;
         const float if_fs = (float)(c->cfg.rf_Fs / c->cfg.rf_decim);
@@ -241,11 +280,15 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch) {
             a.loop[1].coef = cr::pll_coef(114e3f, (float)c->cfg.if_Fs, 0.5f, 0.0f, 0.001f);  // src/rds.cpp:119
         }
         dim3 grid((S + kPllThreads - 1) / kPllThreads, c->rds ? 2 : 1);
-        k_pll<<<grid, kPllThreads, 0, c->stream>>>(a);
-        if ((rc = check_launch(c, "k_pll"))) return rc;
+        k_pll<<<grid, kPllThreads, 0, sp>>>(a);
+        if ((rc = check_launch(c, "k_pll", sp))) return rc;
+    }
+    if (ov) {
+        CU(cudaEventRecord(c->ev_pll[b % kNRing], sp));
+        CU(cudaStreamWaitEvent(sb, c->ev_pll[b % kNRing], 0));
     }
     if (c->stereo) {
-        ScopedTimer tm(c, "mix");
+        ScopedTimer tm(c, "mix", sb);
         MixArgs a{};
         a.n = n_if; a.n_streams = S; a.do_stereo = 1;
         a.band = c->sband.cur(b); a.band_pitch = c->sband.pitch;
@@ -261,11 +304,11 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch) {
             a.delay_out = keep ? c->d_rdelay : nullptr;
         }
         dim3 grid((n_if + 1 + 255) / 256, S);
-        k_mix<<<grid, 256, 0, c->stream>>>(a);
-        if ((rc = check_launch(c, "k_mix"))) return rc;
+        k_mix<<<grid, 256, 0, sb>>>(a);
+        if ((rc = check_launch(c, "k_mix", sb))) return rc;
     }
     {
-        ScopedTimer tm(c, "audio");
+        ScopedTimer tm(c, "audio", sb);
         AudioArgs a{};
         // stereo(): mono path = 50-sample all-pass delay of fm_demod (src/stereo.cpp:88); mono(): fm_demod itself
         a.mono_x = c->fm.cur(b) - (c->stereo ? 50 : 0);
@@ -274,21 +317,21 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch) {
         a.dc_pitch = c->sdc.pitch;
         a.n_in = n_if; a.n_out = c->info.audio_block; a.up = c->up; a.down = c->down;
         a.taps_pm = c->d_audio_pm;
-        a.pcm = c->d_pcm; a.pcm_pitch = c->pcm_pitch;
+        a.pcm = c->d_pcm[b & 1]; a.pcm_pitch = c->pcm_pitch;
         a.mono_out = keep ? c->d_mono : nullptr;
         a.dc_out = keep ? c->d_sfilt : nullptr;
-        if (c->up == 1 && c->down == 5) rc = launch_audio_decim<5>(c, a);
-        else if (c->up == 1 && c->down == 9) rc = launch_audio_decim<9>(c, a);
+        if (c->up == 1 && c->down == 5) rc = launch_audio_decim<5>(c, a, sb);
+        else if (c->up == 1 && c->down == 9) rc = launch_audio_decim<9>(c, a, sb);
         else {
             dim3 grid((a.n_out + 127) / 128, S);
-            if (c->stereo) k_audio_updown<true><<<grid, 128, 0, c->stream>>>(a);
-            else k_audio_updown<false><<<grid, 128, 0, c->stream>>>(a);
-            rc = check_launch(c, "k_audio_updown");
+            if (c->stereo) k_audio_updown<true><<<grid, 128, 0, sb>>>(a);
+            else k_audio_updown<false><<<grid, 128, 0, sb>>>(a);
+            rc = check_launch(c, "k_audio_updown", sb);
         }
         if (rc) return rc;
     }
     if (c->rds) {
-        ScopedTimer tm(c, "rds_backend");
+        ScopedTimer tm(c, "rds_backend", sb);
         RdsArgs a{};
         a.dc = c->rdc.cur(b); a.dc_pitch = c->rdc.pitch;
         a.n_in = n_if; a.n_out = c->info.rds_block; a.sps = 39; a.rds_on = c->cfg.rds_on;
@@ -297,15 +340,16 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch) {
         a.filt_state_in = c->d_filt_state[b & 1];
         a.filt_state_out = c->d_filt_state[(b + 1) & 1];
         a.st = c->d_rds_state;
-        a.rec = c->d_rec;
+        a.rec = c->d_rec[b & 1];
         a.filt_out = keep ? c->d_rfilt : nullptr;
         a.clean_out = keep ? c->d_rclean : nullptr;
         const int rrc_tiles = (a.n_out + kRrcTile - 1) / kRrcTile;
         const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;
         const size_t smem = sizeof(float) * (round_up(n_if + kState, 4) + nfilt + nfilt / kRrcR + 8);
-        k_rds_backend<<<S, kRdsThreads, smem, c->stream>>>(a);
-        if ((rc = check_launch(c, "k_rds_backend"))) return rc;
+        k_rds_backend<<<S, kRdsThreads, smem, sb>>>(a);
+        if ((rc = check_launch(c, "k_rds_backend", sb))) return rc;
     }
+    if (ov) CU(cudaEventRecord(c->ev_back[b % kNRing], sb));
     c->block = b + 1;
     return SDRB_OK;
 }
@@ -344,8 +388,16 @@ int sdrb_config_for_mode(int mode, int type, int n_streams, sdrb_config* cfg) {
 int sdrb_chain_destroy(sdrb_chain* c) {
     if (!c) return SDRB_OK;
     cudaSetDevice(c->cfg.device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (cudaStream_t st : {c->s_front, c->s_pll, c->s_back, c->s_h2d, c->s_d2h, c->stream})
+        if (st) cudaStreamSynchronize(st);
     for (void* p : c->allocs) cudaFree(p);
+    for (cudaStream_t st : {c->s_front, c->s_pll, c->s_back, c->s_h2d, c->s_d2h})
+        if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t e : {c->ev_in, c->ev_join, c->ev_h2d[0], c->ev_h2d[1]})
+        if (e) cudaEventDestroy(e);
+    for (int i = 0; i < kNRing; i++)
+        for (cudaEvent_t e : {c->ev_front[i], c->ev_pll[i], c->ev_back[i]})
+            if (e) cudaEventDestroy(e);
     for (auto& t : c->timed) {
         cudaEventDestroy(t.e0);
         cudaEventDestroy(t.e1);
@@ -413,6 +465,11 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
 
     TRYCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    for (cudaStream_t* st : {&c->s_front, &c->s_pll, &c->s_back, &c->s_h2d, &c->s_d2h})
+        TRYCU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&c->ev_in, &c->ev_join, &c->ev_h2d[0], &c->ev_h2d[1]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (int i = 0; i < kNRing; i++)
+        for (cudaEvent_t* e : {&c->ev_front[i], &c->ev_pll[i], &c->ev_back[i]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 
     // ---- taps (all designed on the host, same libm as the reference build)
     std::vector<float> h(kTaps);
@@ -481,7 +538,7 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         TRY(dalloc(c, (void**)&c->d_pll[1], sizeof(PllStateDev) * S));
         for (int i = 0; i < 2; i++) TRY(dalloc(c, (void**)&c->d_filt_state[i], sizeof(float) * kState * S));
         TRY(dalloc(c, (void**)&c->d_rds_state, sizeof(RdsStreamState) * S));
-        TRY(dalloc(c, (void**)&c->d_rec, sizeof(RdsRecord) * S));
+        for (int i = 0; i < 2; i++) TRY(dalloc(c, (void**)&c->d_rec[i], sizeof(RdsRecord) * S));
     }
     {   // PLL initial state: feedbackI = 1, rest 0 (src/stereo.cpp:51-57, src/rds.cpp:51-56)
         std::vector<PllStateDev> init(S, PllStateDev{1.0f, 0.0f, 0.0f, 0.0f, 0.0});
@@ -496,7 +553,7 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         TRYCU(cudaStreamSynchronize(c->stream));
     }
     c->pcm_pitch = round_up((size_t)I.pcm_per_block, 8);
-    TRY(dalloc(c, (void**)&c->d_pcm, sizeof(int16_t) * c->pcm_pitch * S));
+    for (int i = 0; i < 2; i++) TRY(dalloc(c, (void**)&c->d_pcm[i], sizeof(int16_t) * c->pcm_pitch * S));
     if (cfg->keep_stages) {
         TRY(dalloc(c, (void**)&c->d_ids, sizeof(float) * n_if * S));
         TRY(dalloc(c, (void**)&c->d_qds, sizeof(float) * n_if * S));
@@ -536,27 +593,50 @@ int sdrb_chain_process_device(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitc
     if (iq_pitch < (size_t)c->info.block_bytes || (iq_pitch & 1)) return fail(SDRB_ERR_INVALID, "iq_pitch too small or odd");
     if ((reinterpret_cast<uintptr_t>(d_iq) & 1)) return fail(SDRB_ERR_INVALID, "d_iq must be 2-byte aligned");
     CU(cudaSetDevice(c->cfg.device));
-    return process_block(c, d_iq, iq_pitch);
+    return process_block(c, d_iq, iq_pitch, nullptr);
 }
 
 int sdrb_chain_process_host(sdrb_chain* c, const uint8_t* h_iq, size_t iq_pitch) {
     if (!c || !h_iq) return fail(SDRB_ERR_INVALID, "null argument");
     if (iq_pitch < (size_t)c->info.block_bytes) return fail(SDRB_ERR_INVALID, "iq_pitch too small");
     CU(cudaSetDevice(c->cfg.device));
-    uint8_t* dst = c->d_iq[c->block & 1];
-    CU(cudaMemcpy2DAsync(dst, c->iq_pitch, h_iq, iq_pitch, c->info.block_bytes, c->S, cudaMemcpyHostToDevice, c->stream));
-    return process_block(c, dst, c->iq_pitch);
+    const long long b = c->block;
+    uint8_t* dst = c->d_iq[b & 1];
+    if (!c->overlap) {
+        CU(cudaMemcpy2DAsync(dst, c->iq_pitch, h_iq, iq_pitch, c->info.block_bytes, c->S, cudaMemcpyHostToDevice, c->stream));
+        return process_block(c, dst, c->iq_pitch, nullptr);
+    }
+    // copy engine stream: the staging buffer of parity b was last read by the front end of block b-2
+    if (b >= 2) CU(cudaStreamWaitEvent(c->s_h2d, c->ev_front[(b - 2) % kNRing], 0));
+    CU(cudaEventRecord(c->ev_in, c->stream));
+    CU(cudaStreamWaitEvent(c->s_h2d, c->ev_in, 0));
+    CU(cudaMemcpy2DAsync(dst, c->iq_pitch, h_iq, iq_pitch, c->info.block_bytes, c->S, cudaMemcpyHostToDevice, c->s_h2d));
+    CU(cudaEventRecord(c->ev_h2d[b & 1], c->s_h2d));
+    c->pending = true;
+    return process_block(c, dst, c->iq_pitch, c->ev_h2d[b & 1]);
+}
+
+int sdrb_chain_join(sdrb_chain* c) {
+    if (!c) return fail(SDRB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    return join_main(c);
 }
 
 int sdrb_chain_sync(sdrb_chain* c) {
     if (!c) return fail(SDRB_ERR_INVALID, "null argument");
     CU(cudaSetDevice(c->cfg.device));
+    int rc = join_main(c);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     return SDRB_OK;
 }
 
 int sdrb_chain_set_overlap(sdrb_chain* c, int on) {
     if (!c) return fail(SDRB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = join_main(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));  // switching modes between blocks: nothing may be in flight
     c->overlap = on != 0;
     return SDRB_OK;
 }
@@ -564,6 +644,8 @@ int sdrb_chain_set_overlap(sdrb_chain* c, int on) {
 int sdrb_chain_set_stream(sdrb_chain* c, void* stream) {
     if (!c) return fail(SDRB_ERR_INVALID, "null argument");
     CU(cudaSetDevice(c->cfg.device));
+    int rc = join_main(c);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     if (c->own_stream) {
         cudaStreamDestroy(c->stream);
@@ -584,32 +666,44 @@ int sdrb_pinned_free(void* h_ptr) {
     return SDRB_OK;
 }
 
+// Results of block (most recent - lag), lag 0 or 1.  With lag 1 only the back end of that block is waited for, so the
+// device-to-host copies overlap the block in flight (outputs are double buffered by block parity).
+int sdrb_chain_read_results(sdrb_chain* c, int lag, int16_t* h_pcm, size_t pcm_pitch, sdrb_rds_record* h_records) {
+    if (!c) return fail(SDRB_ERR_INVALID, "null argument");
+    if (lag < 0 || lag > 1) return fail(SDRB_ERR_INVALID, "lag must be 0 or 1");
+    if (c->block - lag <= 0) return fail(SDRB_ERR_STATE, "that block has not been processed yet");
+    if (h_pcm && pcm_pitch < (size_t)c->info.pcm_per_block) return fail(SDRB_ERR_INVALID, "pcm_pitch too small");
+    if (h_records && !c->rds) return fail(SDRB_ERR_STATE, "chain was created without RDS (type != 'r')");
+    CU(cudaSetDevice(c->cfg.device));
+    const long long b = c->block - 1 - lag;
+    cudaStream_t st = c->stream;
+    if (c->overlap) {
+        st = c->s_d2h;
+        CU(cudaStreamWaitEvent(st, c->ev_back[b % kNRing], 0));
+    }
+    if (h_pcm)
+        CU(cudaMemcpy2DAsync(h_pcm, pcm_pitch * sizeof(int16_t), c->d_pcm[b & 1], c->pcm_pitch * sizeof(int16_t),
+                             c->info.pcm_per_block * sizeof(int16_t), c->S, cudaMemcpyDeviceToHost, st));
+    if (h_records) CU(cudaMemcpyAsync(h_records, c->d_rec[b & 1], sizeof(RdsRecord) * c->S, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SDRB_OK;
+}
+
 int sdrb_chain_read_pcm(sdrb_chain* c, int16_t* h_pcm, size_t pcm_pitch) {
     if (!c || !h_pcm) return fail(SDRB_ERR_INVALID, "null argument");
-    if (c->block == 0) return fail(SDRB_ERR_STATE, "no block processed yet");
-    if (pcm_pitch < (size_t)c->info.pcm_per_block) return fail(SDRB_ERR_INVALID, "pcm_pitch too small");
-    CU(cudaSetDevice(c->cfg.device));
-    CU(cudaMemcpy2DAsync(h_pcm, pcm_pitch * sizeof(int16_t), c->d_pcm, c->pcm_pitch * sizeof(int16_t),
-                         c->info.pcm_per_block * sizeof(int16_t), c->S, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return SDRB_OK;
+    return sdrb_chain_read_results(c, 0, h_pcm, pcm_pitch, nullptr);
 }
 
 int sdrb_chain_pcm_device(sdrb_chain* c, const int16_t** d_pcm, size_t* pcm_pitch) {
     if (!c || !d_pcm || !pcm_pitch) return fail(SDRB_ERR_INVALID, "null argument");
-    *d_pcm = c->d_pcm;
+    *d_pcm = c->d_pcm[(c->block > 0 ? c->block - 1 : 0) & 1];
     *pcm_pitch = c->pcm_pitch;
     return SDRB_OK;
 }
 
 int sdrb_chain_read_rds(sdrb_chain* c, sdrb_rds_record* h_records) {
     if (!c || !h_records) return fail(SDRB_ERR_INVALID, "null argument");
-    if (!c->rds) return fail(SDRB_ERR_STATE, "chain was created without RDS (type != 'r')");
-    if (c->block == 0) return fail(SDRB_ERR_STATE, "no block processed yet");
-    CU(cudaSetDevice(c->cfg.device));
-    CU(cudaMemcpyAsync(h_records, c->d_rec, sizeof(RdsRecord) * c->S, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return SDRB_OK;
+    return sdrb_chain_read_results(c, 0, nullptr, 0, h_records);
 }
 
 // parse(), /root/reference/src/rds_utilities.cpp:172-199 (+ stringify :111-119): "PI: " in lower-case hex
@@ -683,6 +777,7 @@ int sdrb_chain_stage(sdrb_chain* c, const char* name, float* h_out, int cap_per_
     *count = n;
     if (cap_per_stream < n) return fail(SDRB_ERR_INVALID, "cap_per_stream too small");
     CU(cudaSetDevice(c->cfg.device));
+    if (int rcj = join_main(c)) return rcj;
     CU(cudaMemcpy2DAsync(h_out, (size_t)cap_per_stream * sizeof(float), src, pitch * sizeof(float), (size_t)n * sizeof(float),
                          c->S, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -730,6 +825,7 @@ size_t sdrb_chain_state_bytes(const sdrb_chain* c) {
 int sdrb_chain_state_save(sdrb_chain* c, void* h_blob) {
     if (!c || !h_blob) return fail(SDRB_ERR_INVALID, "null argument");
     CU(cudaSetDevice(c->cfg.device));
+    if (int rcj = join_main(c)) return rcj;
     CU(cudaStreamSynchronize(c->stream));
     StateHeader hd{kStateMagic, (uint32_t)c->S, (uint32_t)c->info.if_block, (uint32_t)c->cfg.type, c->block};
     char* p = static_cast<char*>(h_blob);
@@ -745,6 +841,7 @@ int sdrb_chain_state_save(sdrb_chain* c, void* h_blob) {
 int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob) {
     if (!c || !h_blob) return fail(SDRB_ERR_INVALID, "null argument");
     CU(cudaSetDevice(c->cfg.device));
+    if (int rcj = join_main(c)) return rcj;
     CU(cudaStreamSynchronize(c->stream));
     StateHeader hd;
     const char* p = static_cast<const char*>(h_blob);
@@ -770,6 +867,7 @@ int sdrb_chain_set_profiling(sdrb_chain* c, int on) {
 int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int cap, int* n) {
     if (!c || !names || !ms || !n) return fail(SDRB_ERR_INVALID, "null argument");
     CU(cudaSetDevice(c->cfg.device));
+    if (int rcj = join_main(c)) return rcj;
     CU(cudaStreamSynchronize(c->stream));
     int k = 0;
     for (auto& t : c->timed) {

@@ -146,3 +146,38 @@ def test_errors_are_reported_not_fatal(capi):
             ch.read_rds()              # no RDS in a mono chain
         with pytest.raises(capi.SdrError):
             ch.process_host(np.zeros((1, 100), np.uint8), 100)  # pitch smaller than a block
+
+
+def test_overlap_pipelined_lagged_reads(capi, oracle, station_iq):
+    """Overlap mode driven the way bench.py's e2e loop drives it: block i is issued before the results of block i-1
+    are read (lag 1); three streams of different stations, host input, 30 blocks."""
+    nblocks, S = 30, 3
+    iqs = [station_iq(k, 0, nblocks) for k in range(S)]
+    wants = [oracle.chain(0, "r", iqs[k]) for k in range(S)]
+    with capi.Chain(0, "r", n_streams=S) as ch:
+        ch.set_overlap(True)
+        bb = ch.info.block_bytes
+        bufs = [np.stack([iqs[s][b * bb:(b + 1) * bb] for s in range(S)]) for b in range(nblocks)]
+        pcm = np.zeros((S, ch.info.pcm_per_block), np.int16)
+        rec = np.zeros(S, capi.RDS_RECORD_DTYPE)
+        got_pcm = [[] for _ in range(S)]
+        got_bits = [[] for _ in range(S)]
+        got_groups = [[] for _ in range(S)]
+
+        def take():
+            for s in range(S):
+                got_pcm[s].append(pcm[s].copy())
+                got_bits[s].append(rec[s]["bits"][: rec[s]["n_bits"]].astype(np.int32))
+                got_groups[s].extend(int(g) for g in rec[s]["groups"][: rec[s]["n_groups"]])
+
+        ch.process_host(bufs[0])
+        for b in range(1, nblocks):
+            ch.process_host(bufs[b])
+            ch.read_results(1, pcm, rec)
+            take()
+        ch.read_results(0, pcm, rec)
+        take()
+    for s in range(S):
+        assert np.array_equal(np.concatenate(got_pcm[s]), wants[s]["pcm"]), s
+        assert np.array_equal(np.concatenate(got_bits[s]), wants[s]["rds_bits"]), s
+        assert np.array_equal(np.array(got_groups[s], np.uint64), wants[s]["groups"]), s
