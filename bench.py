@@ -158,13 +158,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def build_inputs(torch, gen, n_streams, bb, pitch, dev):
+def build_inputs(torch, gen, n_streams, bb, pitch, dev, first_station=0):
     """N_INPUTS step inputs [n_streams][pitch] on the device.  Stream s plays station s % N_STATIONS, delayed by
     s // N_STATIONS blocks, so that no two streams of a step read the same bytes at the same time."""
     bp = bb // 2
     src = np.stack([gen.generate_iq(gen.Station.for_stream(k), bp * N_INPUTS).reshape(N_INPUTS, bb) for k in range(N_STATIONS)])
     src_d = torch.from_numpy(src).to(dev)  # [station][block][bb]
-    s = torch.arange(n_streams, device=dev)
+    s = torch.arange(n_streams, device=dev) + first_station  # global station index (rank r owns a contiguous range)
     inputs = []
     for g in range(N_INPUTS):
         buf = torch.empty((n_streams, pitch), dtype=torch.uint8, device=dev)
@@ -224,7 +224,9 @@ def main():
     stream = torch.cuda.current_stream()
     ch.set_stream(stream.cuda_stream)
     ch.set_overlap(True)
-    inputs = build_inputs(torch, gen, S, bb, pitch, dev)
+    shard = load_mod("sdrb_shard", "real-time-sdr_b200/shard.py")
+    mine = shard.station_range(rank, world, world * S)  # weak scaling: S stations per rank
+    inputs = build_inputs(torch, gen, S, bb, pitch, dev, first_station=mine.start)
     torch.cuda.synchronize()
 
     def barrier():
