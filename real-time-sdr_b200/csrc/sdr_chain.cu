@@ -280,7 +280,7 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
             a.loop[1].coef = cr::pll_coef(114e3f, (float)c->cfg.if_Fs, 0.5f, 0.0f, 0.001f);  // src/rds.cpp:119
         }
         dim3 grid((S + kPllThreads - 1) / kPllThreads, c->rds ? 2 : 1);
-        k_pll<<<grid, kPllThreads, 0, sp>>>(a);
+        k_pll<<<grid, kPllThreads, kPllSmemBytes, sp>>>(a);
         if ((rc = check_launch(c, "k_pll", sp))) return rc;
     }
     if (ov) {
@@ -569,6 +569,8 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
             TRY(dalloc(c, (void**)&c->d_rclean, sizeof(float) * I.rds_block * S));
         }
     }
+    static_assert(kPllTileBytes <= kPllSmemBytes, "PLL input ring must fit the reserved shared memory");
+    if (c->stereo) TRYCU(cudaFuncSetAttribute(k_pll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
     if (c->rds) {
         const int rrc_tiles = (I.rds_block + kRrcTile - 1) / kRrcTile;
         const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;

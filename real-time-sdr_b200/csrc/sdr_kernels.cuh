@@ -290,7 +290,7 @@ struct PllArgs {
     int n_streams;
 };
 
-constexpr int kPllThreads = 32;
+constexpr int kPllThreads = 128;  // four warps = one per SM sub-partition: each has a scheduler (and FP64 lanes) to itself
 
 // 1/(double)v to ~2^-40 relative (MUFU.RCP64H seed + one Newton step); v = 0 or subnormal gives inf/NaN, which
 // the caller's |w| test turns into the general path.  Only ~2^-25 is needed (see pll_step_fast).
@@ -302,9 +302,17 @@ __device__ __forceinline__ double pll_recip(float v) {
 
 constexpr int kPllTileChunks = 8;  // 32 steps per staged tile
 
+constexpr int kPllTileRow = 4 * kPllTileChunks + 4;
+constexpr size_t kPllTileBytes = sizeof(float) * 3 * kPllThreads * kPllTileRow;
+// The launch asks for (nearly) all of an SM's shared memory, far more than the input ring needs: no other CTA then fits
+// on that SM, so in overlap mode the FIR kernels of the neighbouring blocks cannot steal issue slots from the four
+// latency-bound warps (1024 streams x 2 loops = 16 CTAs = 16 of 148 SMs).
+constexpr size_t kPllSmemBytes = 225 * 1024;
+
 __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
     __shared__ cr::AtanTab tab;
-    __shared__ __align__(16) float tile[3][kPllThreads][4 * kPllTileChunks + 4];
+    extern __shared__ __align__(16) float pll_dyn_smem[];
+    float (*tile)[kPllThreads][kPllTileRow] = reinterpret_cast<float (*)[kPllThreads][kPllTileRow]>(pll_dyn_smem);
     {
         const cr::AtanTab init = SDRB_ATAN_TAB_INIT;
         if (threadIdx.x < 17) {
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
         if (g % kPllTileChunks == 0) {
             issue_tile(g / kPllTileChunks + 2);
             asm volatile("cp.async.wait_group 1;" ::: "memory");  // tiles t and t+1 have landed
-            __syncwarp();
+            __syncwarp();  // a lane only ever reads the row it filled itself
             if (g == 0) {
                 vc = chunk_at(0);
                 q0 = pll_recip(vc.x); q1 = pll_recip(vc.y); q2 = pll_recip(vc.z); q3 = pll_recip(vc.w);
