@@ -193,7 +193,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_run(nblocks=98, steps=args.steps, warmup=min(args.warmup, 1))
+        r = cpu_reference_run(nblocks=98, steps=args.steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": round(r["value"], 3), "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

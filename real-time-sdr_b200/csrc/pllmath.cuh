@@ -163,23 +163,23 @@ constexpr double kReduceLimit = 3.0e9;  // |x| below this: k < 2^31, exact Cody-
 // rounds with relative error 2^-53; step 4 adds k*2^-122 absolute.  |r| stays >= 2^-30 for every
 // float below kReduceLimit (checked exhaustively, tests/test_pllmath.py), so r is good to ~2^-53
 // relative; the callers still send |r| < 2^-30 to the slow tier.
-// sin r and cos r for |r| <= pi/4 (+ a little), Taylor through r^17 / r^18, Estrin evaluation.
+// sin r and cos r for |r| <= pi/4: the degree-13 / degree-12 minimax kernels of fdlibm (k_sin.c, k_cos.c: S1..S6,
+// C1..C6, approximation error below 2^-58), evaluated Estrin-style so the dependent depth is z, z^2, z^4 and two fmas.
+// Far inside the 2^-45 the callers allow before they consult the double-double tier.
 SDRB_HD void sincos_poly(double r, double& sr, double& cr_) {
-    double z = dmul(r, r);
-    double z2 = dmul(z, z), z4 = dmul(z2, z2);
-    // sin r = r + r z (S1 + S2 z + ... + S8 z^7),  Sj = (-1)^j / (2j+1)!
-    double sa = dfma(0x1.1111111111111p-7, z, -0x1.5555555555555p-3);    //  1/120, -1/6
-    double sb = dfma(0x1.71de3a556c734p-19, z, -0x1.a01a01a01a01ap-13);  //  1/362880, -1/5040
-    double sc = dfma(0x1.6124613a86d09p-33, z, -0x1.ae64567f544e4p-26);  //  1/6227020800, -1/39916800
-    double sd = dfma(0x1.952c77030ad4ap-49, z, -0x1.ae7f3e733b81fp-41);  //  1/355687428096000, -1/1307674368000
-    double sp = dfma(dfma(sd, z2, sc), z4, dfma(sb, z2, sa));
+    const double z = dmul(r, r);
+    const double z2 = dmul(z, z), z4 = dmul(z2, z2);
+    // sin r = r + r z (S1 + S2 z + S3 z^2 + S4 z^3 + S5 z^4 + S6 z^5)
+    const double s12 = dfma(8.33333333332248946124e-03, z, -1.66666666666666324348e-01);
+    const double s34 = dfma(2.75573137070700676789e-06, z, -1.98412698298579493134e-04);
+    const double s56 = dfma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08);
+    const double sp = dfma(z4, s56, dfma(z2, s34, s12));
     sr = dfma(dmul(r, z), sp, r);
-    // cos r = 1 - z/2 + z^2 (C2 + C3 z + ... + C9 z^7),  Cj = (-1)^j / (2j)!
-    double ca = dfma(-0x1.6c16c16c16c17p-10, z, 0x1.5555555555555p-5);   // -1/720, 1/24
-    double cb = dfma(-0x1.27e4fb7789f5cp-22, z, 0x1.a01a01a01a01ap-16);  // -1/3628800, 1/40320
-    double cc = dfma(-0x1.93974a8c07c9dp-37, z, 0x1.1eed8eff8d898p-29);  // -1/87178291200, 1/479001600
-    double cd = dfma(-0x1.6827863b97d97p-53, z, 0x1.ae7f3e733b81fp-45);  // -1/6402373705728000, 1/20922789888000
-    double cp = dfma(dfma(cd, z2, cc), z4, dfma(cb, z2, ca));
+    // cos r = 1 - z/2 + z^2 (C1 + C2 z + C3 z^2 + C4 z^3 + C5 z^4 + C6 z^5)
+    const double c12 = dfma(-1.38888888888741095749e-03, z, 4.16666666666666019037e-02);
+    const double c34 = dfma(-2.75573143513906633035e-07, z, 2.48015872894767294178e-05);
+    const double c56 = dfma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09);
+    const double cp = dfma(z4, c56, dfma(z2, c34, c12));
     cr_ = dfma(z2, cp, dfma(-0.5, z, 1.0));
 }
 SDRB_HD double flip_sign_if(double v, unsigned flip) {  // exact negation by a sign-bit XOR (one integer op on the chain)
@@ -553,8 +553,10 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     const double xd = dadd(vt, -dadd(vt, -td));
     bad |= (unsigned)!(fabs(td) < kReduceLimit) | (unsigned)!(fabs(td) > 0x1p-100) |
            (unsigned)(((uint32_t)dbits(td) & 0x1FFFFFFFu) == 0x10000000u);
-    // quarter-turn reduction and polynomials (sincos_reduced, inlined so that its test joins `bad`)
-    const double tm = dfma(xd, kTwoOverPi, kMagicRint);
+    // quarter-turn reduction and polynomials (sincos_reduced, inlined so that its test joins `bad`).  The quadrant
+    // count only needs x approximately, so it is taken from td and runs beside the split above, not after it; where
+    // td and xd would round to different k the reduced argument merely ends a hair outside pi/4.
+    const double tm = dfma(td, kTwoOverPi, kMagicRint);
     const double kd = dadd(tm, -kMagicRint);
     const int q = (int)(uint32_t)dbits(tm) & 3;
     double r = dfma(-kd, kP2, dfma(-kd, kP1, xd));
