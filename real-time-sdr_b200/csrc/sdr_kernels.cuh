@@ -59,8 +59,23 @@ __device__ __forceinline__ int pad_pos(int u) {
 }
 
 __device__ __forceinline__ float mac(float acc, float h, float x) { return __fadd_rn(acc, __fmul_rn(h, x)); }
+// Two channels at once on Blackwell's packed FP32 pipe (FFMA2 / FADD2), keeping the two roundings of the bit-exact MAC.
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into ONE FFMA2 (one rounding) even under -fmad=false and even when the
+// multiply is spelled fma(h, x, -0) with a literal -0, so the product is formed as fma(h, x, nz) with nz = (-0, -0) read
+// from a run-time constant the compiler cannot fold: RN(h*x - 0) = RN(h*x) exactly (and the sign of a zero product is
+// kept), followed by a separate FADD2.  Two instructions per two MACs instead of four.
+__device__ __constant__ unsigned long long c_neg_zero2 = 0x8000000080000000ull;
+
 __device__ __forceinline__ float2 mac(float2 acc, float h, float2 x) {
-    return make_float2(__fadd_rn(acc.x, __fmul_rn(h, x.x)), __fadd_rn(acc.y, __fmul_rn(h, x.y)));
+    unsigned long long a, xx, hh, p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(acc.x), "f"(acc.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x.x), "f"(x.y));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(h));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(hh), "l"(xx), "l"(c_neg_zero2));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(a), "l"(p));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a));
+    return r;
 }
 
 // y[m] = sum_k h[k] * x[D*m - k]   for the R outputs m = R*lane + j of this lane.

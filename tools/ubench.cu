@@ -39,7 +39,7 @@ __global__ void lat_kernel(double seed, long long* cycles, double* sink) {
 // throughput: NACC independent accumulators per thread, MODE 0: FMUL+FADD scalar, 1: FFMA scalar,
 // 2: mul.f32x2 + add.f32x2, 3: fma.f32x2
 template <int MODE>
-__global__ void tput_kernel(float seed, long long* cycles, float* sink) {
+__global__ void tput_kernel(float seed, long long* cycles, float* sink, unsigned long long nz) {
     constexpr int NACC = 16;
     float a[NACC];
     float h = 1.0f + seed * 1e-6f;
@@ -58,13 +58,15 @@ __global__ void tput_kernel(float seed, long long* cycles, float* sink) {
 #pragma unroll
                 for (int j = 0; j < NACC; j++) a[j] = __fmaf_rn(h, a[j], x);
             } else if (MODE == 2) {
+                // unfused packed MAC: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even with -fmad=false), so
+                // the product is formed as fma(h, x, nz) with nz = (-0, -0) passed at run time: RN(h*x) exactly, not foldable
 #pragma unroll
                 for (int j = 0; j < NACC; j += 2) {
                     unsigned long long acc, hh, xx, p;
                     asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(a[j]), "f"(a[j + 1]));
-                    asm("mov.b64 %0, {%1, %2};" : "=l"(hh) : "f"(h + (float)j), "f"(h + (float)(j + 1)));
-                    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
-                    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(hh), "l"(xx));
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(h));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x), "f"(a[(j + 3) % NACC]));
+                    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(hh), "l"(xx), "l"(nz));
                     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(acc), "l"(p));
                     asm("mov.b64 {%0, %1}, %2;" : "=f"(a[j]), "=f"(a[j + 1]) : "l"(acc));
                 }
@@ -108,8 +110,8 @@ int run_tput(const char* name, int warps_per_sm) {
     long long* cyc; float* sink;
     int threads = 32 * warps_per_sm;
     CK(cudaMalloc(&cyc, 8 * 148)); CK(cudaMalloc(&sink, 4 * 148 * threads));
-    tput_kernel<MODE><<<148, threads>>>(1.5f, cyc, sink);
-    tput_kernel<MODE><<<148, threads>>>(1.5f, cyc, sink);
+    tput_kernel<MODE><<<148, threads>>>(1.5f, cyc, sink, 0x8000000080000000ull);
+    tput_kernel<MODE><<<148, threads>>>(1.5f, cyc, sink, 0x8000000080000000ull);
     CK(cudaDeviceSynchronize());
     long long h[148]; CK(cudaMemcpy(h, cyc, 8 * 148, cudaMemcpyDeviceToHost));
     double mean = 0; for (int i = 0; i < 148; i++) mean += h[i]; mean /= 148;
@@ -128,7 +130,7 @@ int main() {
     run_lat<6>("ddiv_rn+dadd", 2); run_lat<7>("f2f_d2f+f2f_f2d+dadd", 3); run_lat<8>("dmul+drint", 2);
     run_lat<9>("rcp64h+dadd", 2); run_lat<10>("fast_fdiv+fadd", 3); run_lat<11>("lop64+dadd", 2);
     for (int w : {4, 8, 16, 32}) {
-        run_tput<0>("fmul+fadd", w); run_tput<1>("ffma", w); run_tput<2>("mul.f32x2+add.f32x2", w); run_tput<3>("fma.f32x2", w);
+        run_tput<0>("fmul+fadd", w); run_tput<1>("ffma", w); run_tput<2>("ffma2(h,x,-0)+fadd2 (unfused packed MAC)", w); run_tput<3>("fma.f32x2", w);
     }
     return 0;
 }
