@@ -226,6 +226,9 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
         a.fm = c->fm.view(b);
         a.i_ds = keep ? c->d_ids : nullptr;
         a.q_ds = keep ? c->d_qds : nullptr;
+        const size_t bytes16 = round_up((size_t)c->info.block_bytes, 16);
+        a.tma_ok = (reinterpret_cast<uintptr_t>(d_iq) % 16 == 0) && (iq_pitch % 16 == 0) && (iq_pitch >= bytes16);
+        a.row_bytes16 = a.tma_ok ? (int)bytes16 : c->info.block_bytes;
         switch (c->cfg.rf_decim) {
             case 10: rc = launch_rf<10>(c, a, sf); break;
             case 4: rc = launch_rf<4>(c, a, sf); break;

@@ -166,6 +166,8 @@ struct RfArgs {
     RingView fm;             // fm_demod
     float* i_ds;             // optional [n_streams][if_block] (parity tests)
     float* q_ds;
+    int tma_ok;              // iq base and pitch are 16-byte aligned and every row has round_up(block_bytes, 16) readable bytes
+    int row_bytes16;         // round_up(2*block_pairs, 16) when tma_ok, else 2*block_pairs
 };
 
 // (u8 - 128)/128 exactly: 0x4B000000|u is the float 2^23 + u; *2^-7 - 65537 is exact in one FMA.
@@ -181,24 +183,79 @@ __device__ __forceinline__ float fm_discriminate(float I, float Q, float pI, flo
     return __double2float_rn(__ddiv_rn((double)num, den));
 }
 
+// ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the async proxy must see the initialised barrier
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 template <int DECIM>
 __global__ void __launch_bounds__(kRfThreads) k_rf_frontend(const __grid_constant__ Taps101 taps, const RfArgs a) {
     constexpr int L = DECIM * kRfR;
     constexpr int NS = DECIM * (kRfTile - 1) + kTaps;  // input pairs a tile needs
+    constexpr int kRawBytes = (2 * NS + 15 + 16) / 16 * 16;  // the tile's bytes, widened to 16-byte boundaries on both sides
+    constexpr int kRawAlloc = kRawBytes > (int)(sizeof(float2) * kRfTile) ? kRawBytes : (int)(sizeof(float2) * kRfTile);
     __shared__ float2 sx[NS + NS / L + 2];
-    __shared__ float2 sy[kRfTile];
+    __shared__ __align__(16) uint8_t raw[kRawAlloc];  // later reused for the FIR outputs (sy)
+    __shared__ __align__(8) unsigned long long bar;
+    float2* sy = reinterpret_cast<float2*>(raw);  // FIR outputs; the raw bytes are dead by then
     const int s = blockIdx.y;
     const int tile = blockIdx.x;
     const int m0 = tile * (kRfTile - 1) - 1;  // first FIR output of the tile (may be -1)
     const int g0 = DECIM * m0 - kState;       // first input pair (negative: halo)
     const uint8_t* blk = a.iq + (size_t)s * a.iq_pitch;
     const uint8_t* hal = a.halo_in + (size_t)s * (2 * kIqHaloPairs);
+    // Byte window [A, A + span) of the stream row (negative = carried halo), A a multiple of 16.
+    const int byte_lo = 2 * g0;
+    const int A = (byte_lo >= 0) ? (byte_lo & ~15) : -((-byte_lo + 15) & ~15);
+    const int byte_hi = min(2 * (g0 + NS), a.row_bytes16);  // never past the 16-byte-rounded end of the block
+    if (a.tma_ok) {
+        // Staging by TMA: one thread issues the bulk copies (carried halo bytes, then the block bytes), the CTA sleeps
+        // on the mbarrier; no registers or issue slots are spent on the 5.3 KB of input.
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int lo = max(A, 0);
+            const uint32_t nhalo = A < 0 ? (uint32_t)(-A) : 0u;
+            const uint32_t nblk = byte_hi > lo ? (uint32_t)((byte_hi - lo + 15) & ~15) : 0u;
+            mbar_expect_tx(&bar, nhalo + nblk);
+            if (nhalo) tma_load_1d(raw, hal + (2 * kIqHaloPairs + A), nhalo, &bar);
+            if (nblk) tma_load_1d(raw + (lo - A), blk + lo, nblk, &bar);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        // unaligned caller buffer: plain 16-bit loads into the same layout
+        for (int o = 2 * threadIdx.x; o < kRawBytes; o += 2 * kRfThreads) {
+            const int bo = A + o;
+            uint16_t v = 0x8080u;
+            if (bo < 0) { if (bo >= -2 * kIqHaloPairs) v = *reinterpret_cast<const uint16_t*>(hal + 2 * kIqHaloPairs + bo); }
+            else if (bo < 2 * a.block_pairs) v = *reinterpret_cast<const uint16_t*>(blk + bo);
+            *reinterpret_cast<uint16_t*>(raw + o) = v;
+        }
+        __syncthreads();
+    }
+    // unpack to float2 (I, Q) in the padded, bank-conflict-free layout the FIR core reads
     for (int u = threadIdx.x; u < NS; u += kRfThreads) {
-        int g = g0 + u;
-        uint32_t pr;
-        if (g < 0) pr = *reinterpret_cast<const uint16_t*>(hal + 2 * (kIqHaloPairs + g));
-        else if (g < a.block_pairs) pr = *reinterpret_cast<const uint16_t*>(blk + 2 * (size_t)g);
-        else pr = 0x8080u;
+        const int g = g0 + u;
+        uint32_t pr = 0x8080u;  // beyond the block: the byte that unpacks to 0.0f
+        if (g < a.block_pairs) pr = *reinterpret_cast<const uint16_t*>(raw + (2 * g - A));
         sx[pad_pos<L>(u)] = make_float2(unpack_u8(pr & 0xFFu), unpack_u8(pr >> 8));
     }
     // carry the last pairs of this block to the next block's halo (one tile per stream does it)
