@@ -117,27 +117,56 @@ __device__ __forceinline__ void fir_core(const V* __restrict__ sx_lane, const Ta
     }
 }
 
-// NF filters over the same input, D = 1.
+// NF filters over the same input, D = 1, two adjacent outputs per packed accumulator.
+//
+// Output pair p of a lane is (y[R*lane + 2p], y[R*lane + 2p + 1]); tap k needs the input pair that starts at
+// x[R*lane + 2p - k].  For even k that is an even-aligned pair, for odd k an odd-aligned one, so the tile is kept
+// twice in shared memory: E[m] = (x[2m], x[2m+1]) and O[m] = (x[2m+1], x[2m+2]) (u = 0 is the oldest sample,
+// kState before the first output).  Each alignment has its own sliding window of R/2 register pairs that moves by
+// one pair every second tap: two LDS.64 per two taps, all MACs packed (see mac(float2, ...)).  The tap loop is a
+// real loop (period R/2 in q = k/2, the window slots rotate by compile-time indices inside the body): fully
+// unrolled, the 3-filter kernel was 80 KB of code and spent half its cycles waiting for instructions.
+// Pair m lives at position m + m/(R/2): lane stride R/2+1 pairs, conflict free for LDS.64.
 template <int NF, int R>
-__device__ __forceinline__ void fir_bank_core(const float* __restrict__ sx_lane, const Taps101* t, float (&acc)[NF][R]) {
-    constexpr int L = R;
-    float w[R];
+__device__ __forceinline__ void fir_bank_core(const float2* __restrict__ sE_lane, const float2* __restrict__ sO_lane,
+                                              const Taps101* t, float2 (&acc)[NF][R / 2]) {
+    constexpr int HP = R / 2;
+    constexpr int HS = kState / 2;
+    constexpr int NQ = kTaps / 2 + 1;  // q = 0 .. 50: taps 2q and 2q+1
+    static_assert(R % 2 == 0 && kState % 2 == 0, "pairs");
+    float2 wE[HP], wO[HP];
 #pragma unroll
-    for (int j = 0; j < R; j++) {
-        const int c = j + kState;
-        w[j] = sx_lane[c + c / L];
+    for (int p = 0; p < HP; p++) {
+        const int cE = HS + p, cO = HS - 1 + p;
+        wE[p] = sE_lane[cE + cE / HP];
+        wO[p] = sO_lane[cO + cO / HP];
     }
+#pragma unroll 1
+    for (int q0 = 0; q0 < NQ; q0 += HP) {
 #pragma unroll
-    for (int k = 0; k < kTaps; k++) {
-        if (k > 0) {
-            const int c = -k + kState;
-            w[((-k) % R + R) % R] = sx_lane[c + c / L];
-        }
+        for (int qq = 0; qq < HP; qq++) {
+            const int q = q0 + qq;
+            if (2 * q < kTaps) {
 #pragma unroll
-        for (int f = 0; f < NF; f++) {
-            const float hk = t[f].h[k];
+                for (int f = 0; f < NF; f++) {
+                    const float hk = t[f].h[2 * q];
 #pragma unroll
-            for (int j = 0; j < R; j++) acc[f][j] = mac(acc[f][j], hk, w[((j - k) % R + R) % R]);
+                    for (int p = 0; p < HP; p++) acc[f][p] = mac(acc[f][p], hk, wE[((p - qq) % HP + HP) % HP]);
+                }
+            }
+            if (2 * q + 1 < kTaps) {
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    const float hk = t[f].h[2 * q + 1];
+#pragma unroll
+                    for (int p = 0; p < HP; p++) acc[f][p] = mac(acc[f][p], hk, wO[((p - qq) % HP + HP) % HP]);
+                }
+            }
+            // windows for q+1: one new (oldest) pair each, into the slot the newest pair just left
+            const int slot = ((-(qq + 1)) % HP + HP) % HP;
+            const int cE = HS - (q + 1), cO = HS - 2 - q;
+            if (cE >= 0) wE[slot] = sE_lane[cE + cE / HP];
+            if (cO >= 0) wO[slot] = sO_lane[cO + cO / HP];
         }
     }
 }
@@ -307,8 +336,11 @@ struct BankArgs {
 
 template <int NF, bool SQUARE>
 __global__ void __launch_bounds__(32 * kBankWarps) k_fir_bank(const __grid_constant__ BankArgs<NF> a) {
-    constexpr int NS = kBankTile + kState;
-    __shared__ float sx[kBankWarps][NS + NS / kBankR + 1];
+    constexpr int NS = kBankTile + kState;  // samples a tile needs
+    constexpr int HP = kBankR / 2;
+    constexpr int NP = NS / 2 + 1;          // pairs per alignment
+    __shared__ float2 sE[kBankWarps][NP + NP / HP + 1];
+    __shared__ float2 sO[kBankWarps][NP + NP / HP + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * kBankWarps + warp;
     const int s = (int)(wid / a.tiles);
@@ -316,24 +348,32 @@ __global__ void __launch_bounds__(32 * kBankWarps) k_fir_bank(const __grid_const
     if (s >= a.n_streams) return;
     const int n0 = tile * kBankTile;
     const float* xr = a.x + (size_t)s * a.x_pitch + n0 - kState;
-    for (int u = lane; u < NS; u += 32) {
-        float v = (n0 - kState + u < a.n) ? xr[u] : 0.0f;
+    float* fE = reinterpret_cast<float*>(sE[warp]);
+    float* fO = reinterpret_cast<float*>(sO[warp]);
+    for (int u = lane; u < NS + 2; u += 32) {
+        float v = (u < NS && n0 - kState + u < a.n) ? xr[u] : 0.0f;
         if (SQUARE) v = __fmul_rn(v, v);
-        sx[warp][pad_pos<kBankR>(u)] = v;
+        const int mE = u >> 1;
+        if (mE < NP) fE[2 * (mE + mE / HP) + (u & 1)] = v;          // E[m] = (x[2m], x[2m+1])
+        if (u >= 1) {
+            const int mO = (u - 1) >> 1;
+            if (mO < NP) fO[2 * (mO + mO / HP) + ((u - 1) & 1)] = v;  // O[m] = (x[2m+1], x[2m+2])
+        }
     }
     __syncwarp();
-    float acc[NF][kBankR];
+    float2 acc[NF][HP];
 #pragma unroll
     for (int f = 0; f < NF; f++)
 #pragma unroll
-        for (int j = 0; j < kBankR; j++) acc[f][j] = 0.0f;
-    fir_bank_core<NF, kBankR>(&sx[warp][(kBankR + 1) * lane], a.taps, acc);
+        for (int p = 0; p < HP; p++) acc[f][p] = make_float2(0.0f, 0.0f);
+    fir_bank_core<NF, kBankR>(&sE[warp][(HP + 1) * lane], &sO[warp][(HP + 1) * lane], a.taps, acc);
 #pragma unroll
     for (int f = 0; f < NF; f++)
 #pragma unroll
-        for (int j = 0; j < kBankR; j++) {
-            int n = n0 + kBankR * lane + j;
-            if (n < a.n) ring_store(a.y[f], s, n, acc[f][j]);
+        for (int p = 0; p < HP; p++) {
+            const int n = n0 + kBankR * lane + 2 * p;
+            if (n < a.n) ring_store(a.y[f], s, n, acc[f][p].x);
+            if (n + 1 < a.n) ring_store(a.y[f], s, n + 1, acc[f][p].y);
         }
 }
 
