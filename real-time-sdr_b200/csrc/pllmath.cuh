@@ -392,6 +392,7 @@ SDRB_HD float pll_step(float in, PllState& st, const PllCoef& k, const AtanTab& 
 }
 
 // ---- the same recurrence with a short dependency chain (what the batched kernel runs) ----
+// (cos_lean_f, used by the parallel NCO-output kernel, is defined after sincos_reduced below)
 //
 // The phase detector's inputs are errorI = RN(in*feedbackI), errorQ = RN(in*-feedbackQ) with
 // feedbackI/Q = RN_float(cos/sin(theta)) of the PREVIOUS step, so atan2(errorQ, errorI) equals
@@ -437,6 +438,16 @@ SDRB_HD bool sincos_reduced(double x, double& s, double& c, double& r_out, int& 
     r_out = r;
     q_out = q;
     return !((kd != 0.0) && fabs(r) < 0x1p-30);
+}
+
+// cos_f with the leaner reduction: no rint, one acceptance test; anything doubtful goes to cos_f itself
+SDRB_HD float cos_lean_f(float t) {
+    const double x = (double)t;
+    double ds, dc, r;
+    int q;
+    const bool ok = sincos_reduced(x, ds, dc, r, q);
+    if (!(fabs(x) < kReduceLimit) || !ok || near_float_boundary(dc)) return cos_f(t);
+    return (float)dc;
 }
 
 SDRB_HD void pll_fast_sincos(float trigArg, PllFast& f) {

@@ -262,7 +262,7 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
         a.x = c->rband.cur(b); a.x_pitch = c->rband.pitch; a.n = n_if; a.tiles = tiles; a.n_streams = S;
         a.y[0] = c->gpilot.view(b);
         a.taps[0] = c->rds114_h;
-        k_fir_bank<1, true><<<bank_blocks, 32 * kBankWarps, 0, sf>>>(a);
+        k_fir_bank_scalar<1, true><<<bank_blocks, 32 * kBankWarps, 0, sf>>>(a);
         if ((rc = check_launch(c, "k_fir_bank<1,sq>", sf))) return rc;
     }
     if (ov) {
@@ -306,7 +306,7 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
             a.ipll_out = keep ? c->d_ipll : nullptr;
             a.delay_out = keep ? c->d_rdelay : nullptr;
         }
-        dim3 grid((n_if + 1 + 255) / 256, S);
+        dim3 grid((n_if + 1 + 256 * kMixPer - 1) / (256 * kMixPer), S);
         k_mix<<<grid, 256, 0, sb>>>(a);
         if ((rc = check_launch(c, "k_mix", sb))) return rc;
     }

@@ -171,6 +171,32 @@ __device__ __forceinline__ void fir_bank_core(const float2* __restrict__ sE_lane
     }
 }
 
+// Scalar form of the bank core (one output per accumulator, fully unrolled): best for a single filter, where the
+// packed form has too few independent accumulators per thread; its code stays small enough for the I-cache (NF = 1).
+template <int NF, int R>
+__device__ __forceinline__ void fir_bank_core_scalar(const float* __restrict__ sx_lane, const Taps101* t, float (&acc)[NF][R]) {
+    constexpr int L = R;
+    float w[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int c = j + kState;
+        w[j] = sx_lane[c + c / L];
+    }
+#pragma unroll
+    for (int k = 0; k < kTaps; k++) {
+        if (k > 0) {
+            const int c = -k + kState;
+            w[((-k) % R + R) % R] = sx_lane[c + c / L];
+        }
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            const float hk = t[f].h[k];
+#pragma unroll
+            for (int j = 0; j < R; j++) acc[f][j] = mac(acc[f][j], hk, w[((j - k) % R + R) % R]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1  RF front-end: u8 IQ -> unpack -> 101-tap LPF / DECIM on I and Q -> FM discriminator.
 // /root/reference/src/rffrontend.cpp:58-71, src/filter.cpp:106-121, src/demod.cpp:3-24.
@@ -377,6 +403,38 @@ __global__ void __launch_bounds__(32 * kBankWarps) k_fir_bank(const __grid_const
         }
 }
 
+template <int NF, bool SQUARE>
+__global__ void __launch_bounds__(32 * kBankWarps) k_fir_bank_scalar(const __grid_constant__ BankArgs<NF> a) {
+    constexpr int NS = kBankTile + kState;
+    __shared__ float sx[kBankWarps][NS + NS / kBankR + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * kBankWarps + warp;
+    const int s = (int)(wid / a.tiles);
+    const int tile = (int)(wid % a.tiles);
+    if (s >= a.n_streams) return;
+    const int n0 = tile * kBankTile;
+    const float* xr = a.x + (size_t)s * a.x_pitch + n0 - kState;
+    for (int u = lane; u < NS; u += 32) {
+        float v = (n0 - kState + u < a.n) ? xr[u] : 0.0f;
+        if (SQUARE) v = __fmul_rn(v, v);
+        sx[warp][pad_pos<kBankR>(u)] = v;
+    }
+    __syncwarp();
+    float acc[NF][kBankR];
+#pragma unroll
+    for (int f = 0; f < NF; f++)
+#pragma unroll
+        for (int j = 0; j < kBankR; j++) acc[f][j] = 0.0f;
+    fir_bank_core_scalar<NF, kBankR>(&sx[warp][(kBankR + 1) * lane], a.taps, acc);
+#pragma unroll
+    for (int f = 0; f < NF; f++)
+#pragma unroll
+        for (int j = 0; j < kBankR; j++) {
+            int n = n0 + kBankR * lane + j;
+            if (n < a.n) ring_store(a.y[f], s, n, acc[f][j]);
+        }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3  PLL: one lane per stream, strictly sequential in time.  /root/reference/src/pll.cpp:4-61.
 // The NCO output cos(trigArg*ncoScale + phaseAdjust) (:52) is not part of the recurrence, so the
@@ -525,29 +583,44 @@ struct MixArgs {
     int do_stereo;
 };
 
+constexpr int kMixPer = 4;  // consecutive samples per thread: all loads first, then the cosines
+
 __global__ void __launch_bounds__(256) k_mix(const MixArgs a) {
     const int s = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > a.n) return;
-    if (a.do_stereo) {
-        float th = a.trig19[(size_t)s * a.trig19_pitch + i - 1];
-        float car = cr::cos_f(__fadd_rn(__fmul_rn(th, a.scale19), a.adjust19));
-        if (a.carrier_out) a.carrier_out[(size_t)s * (a.n + 1) + i] = car;
-        if (i < a.n) {
-            float b = a.band[(size_t)s * a.band_pitch + i];
-            float v = __double2float_rn(__dmul_rn(__dmul_rn(2.0, (double)b), (double)car));
-            ring_store(a.stereo_dc, s, i, v);
-        }
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * kMixPer;
+    if (i0 > a.n) return;
+    float th19[kMixPer], band[kMixPer], th114[kMixPer], rb[kMixPer];
+    const bool rds = a.rds_band != nullptr;
+#pragma unroll
+    for (int j = 0; j < kMixPer; j++) {
+        const int i = i0 + j;
+        const bool in_car = i <= a.n, in_blk = i < a.n;
+        th19[j] = (a.do_stereo && in_car) ? a.trig19[(size_t)s * a.trig19_pitch + i - 1] : 0.0f;
+        band[j] = (a.do_stereo && in_blk) ? a.band[(size_t)s * a.band_pitch + i] : 0.0f;
+        th114[j] = (rds && in_car) ? a.trig114[(size_t)s * a.trig114_pitch + i - 1] : 0.0f;
+        rb[j] = (rds && in_blk) ? a.rds_band[(size_t)s * a.rds_band_pitch + i - 50] : 0.0f;
     }
-    if (a.rds_band) {
-        float th = a.trig114[(size_t)s * a.trig114_pitch + i - 1];
-        float ip = cr::cos_f(__fadd_rn(__fmul_rn(th, a.scale114), a.adjust114));
-        if (a.ipll_out) a.ipll_out[(size_t)s * (a.n + 1) + i] = ip;
-        if (i < a.n) {
-            // the all-pass "delay" FIR (src/rds.cpp:122): 0 + 1*x[i-50] + 0*... == 0.0f + x[i-50]
-            float d = __fadd_rn(0.0f, a.rds_band[(size_t)s * a.rds_band_pitch + i - 50]);
-            if (a.delay_out) a.delay_out[(size_t)s * a.n + i] = d;
-            ring_store(a.rds_dc, s, i, __fmul_rn(__fmul_rn(2.0f, d), ip));
+#pragma unroll
+    for (int j = 0; j < kMixPer; j++) {
+        const int i = i0 + j;
+        if (i > a.n) break;
+        if (a.do_stereo) {
+            const float car = cr::cos_lean_f(__fadd_rn(__fmul_rn(th19[j], a.scale19), a.adjust19));
+            if (a.carrier_out) a.carrier_out[(size_t)s * (a.n + 1) + i] = car;
+            if (i < a.n) {
+                const float v = __double2float_rn(__dmul_rn(__dmul_rn(2.0, (double)band[j]), (double)car));
+                ring_store(a.stereo_dc, s, i, v);
+            }
+        }
+        if (rds) {
+            const float ip = cr::cos_lean_f(__fadd_rn(__fmul_rn(th114[j], a.scale114), a.adjust114));
+            if (a.ipll_out) a.ipll_out[(size_t)s * (a.n + 1) + i] = ip;
+            if (i < a.n) {
+                // the all-pass "delay" FIR (src/rds.cpp:122): 0 + 1*x[i-50] + 0*... == 0.0f + x[i-50]
+                const float d = __fadd_rn(0.0f, rb[j]);
+                if (a.delay_out) a.delay_out[(size_t)s * a.n + i] = d;
+                ring_store(a.rds_dc, s, i, __fmul_rn(__fmul_rn(2.0f, d), ip));
+            }
         }
     }
 }

@@ -20,6 +20,7 @@ extern "C" {
 
 void crh_sincos(const float* t, int n, float* s, float* c) { for (int i = 0; i < n; i++) sincos_f(t[i], s[i], c[i]); }
 void crh_cos(const float* t, int n, float* c) { for (int i = 0; i < n; i++) c[i] = cos_f(t[i]); }
+void crh_cos_lean(const float* t, int n, float* c) { for (int i = 0; i < n; i++) c[i] = cos_lean_f(t[i]); }
 void crh_atan2(const float* y, const float* x, int n, float* o) { for (int i = 0; i < n; i++) o[i] = atan2_f(y[i], x[i], kTab); }
 
 // force a tier: 0 fast only (no boundary check), 1 slow only

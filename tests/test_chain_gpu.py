@@ -181,3 +181,45 @@ def test_overlap_pipelined_lagged_reads(capi, oracle, station_iq):
         assert np.array_equal(np.concatenate(got_pcm[s]), wants[s]["pcm"]), s
         assert np.array_equal(np.concatenate(got_bits[s]), wants[s]["rds_bits"]), s
         assert np.array_equal(np.array(got_groups[s], np.uint64), wants[s]["groups"]), s
+
+
+def test_full_size_batch_1024_streams(capi, oracle, station_iq):
+    """BASELINE.json configs[4] at full width: 1024 stations (8 distinct ones, each delayed by s // 8 blocks like bench.py
+    builds them) for 24 blocks in overlap mode with lagged reads.  Every one of the 1024 streams must equal the oracle run
+    of its own block sequence: PCM bit for bit and the same RDS bits."""
+    S, nblocks, M, NB = 1024, 24, 8, 8
+    bb = 147000
+    src = np.stack([station_iq(k, 0, NB).reshape(NB, bb) for k in range(M)])  # [station][block][bytes]
+    sidx = np.arange(S)
+
+    def step_input(g):
+        return src[sidx % M, (g + sidx // M) % NB]
+
+    # oracle: stream s sees station s % M starting at block (s // M) % NB, wrapping inside the NB generated blocks
+    want = {}
+    for k in range(M):
+        for d in range(NB):
+            seq = np.concatenate([src[k, (g + d) % NB] for g in range(nblocks)])
+            want[(k, d)] = oracle.chain(0, "r", seq)
+    with capi.Chain(0, "r", n_streams=S) as ch:
+        ch.set_overlap(True)
+        pcm = np.zeros((S, ch.info.pcm_per_block), np.int16)
+        rec = np.zeros(S, capi.RDS_RECORD_DTYPE)
+        all_pcm = np.zeros((nblocks, S, ch.info.pcm_per_block), np.int16)
+        nbits = np.zeros((nblocks, S), np.int32)
+        bits = np.zeros((nblocks, S, 48), np.uint8)
+        bufs = [np.ascontiguousarray(step_input(g)) for g in range(min(nblocks, NB))]
+        ch.process_host(bufs[0])
+        for b in range(1, nblocks):
+            ch.process_host(bufs[b % NB])
+            ch.read_results(1, pcm, rec)
+            all_pcm[b - 1], nbits[b - 1], bits[b - 1] = pcm, rec["n_bits"], rec["bits"]
+        ch.read_results(0, pcm, rec)
+        all_pcm[nblocks - 1], nbits[nblocks - 1], bits[nblocks - 1] = pcm, rec["n_bits"], rec["bits"]
+    bad = []
+    for s in range(S):
+        w = want[(s % M, (s // M) % NB)]
+        got_bits = np.concatenate([bits[b, s, : nbits[b, s]] for b in range(nblocks)]).astype(np.int32)
+        if not np.array_equal(all_pcm[:, s, :].reshape(-1), w["pcm"]) or not np.array_equal(got_bits, w["rds_bits"]):
+            bad.append(s)
+    assert not bad, f"{len(bad)} of {S} streams differ from their oracle run, first: {bad[:8]}"

@@ -144,3 +144,15 @@ def test_fast_recurrence_edge_inputs(host, oracle):
             want, _ = oracle.pll(x, freq, 240000.0, scale, 0.0, bw, nblocks=nb)
             y, _ = _run_fast(host, x, freq, scale, bw, n)
             assert int((y.view(np.uint32) != want.view(np.uint32)).sum()) == 0, (nm, freq)
+
+
+def test_lean_cosine_equals_glibc(host):
+    """cos_lean_f (the NCO-output kernel's cosine) on 4M arguments over the range the scaled NCO phase visits."""
+    host.crh_cos_lean.argtypes = [f32p, C.c_int, f32p]
+    rng = np.random.default_rng(21)
+    t = np.concatenate([(rng.random(2_000_000) * 6e6).astype(np.float32), (rng.random(1_000_000) * 100).astype(np.float32),
+                        -(rng.random(500_000) * 1e4).astype(np.float32), (rng.random(500_000) * 2.9e9).astype(np.float32),
+                        np.array([0.0, -0.0, 1e-30, 3.1415927, 1.5707964, 4e9, 1e20], np.float32)])
+    c = np.zeros_like(t)
+    host.crh_cos_lean(t, t.size, c)
+    assert np.array_equal(c.view(np.uint32), np.cos(t.astype(np.float64)).astype(np.float32).view(np.uint32))
