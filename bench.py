@@ -297,11 +297,24 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
                 "kernel_ms": {k: round(v, 4) for k, v in kernel_ms.items()},
                 "note": "the chain is FP32-issue / latency bound, not HBM bound (DESIGN.md section 5): see fp32"}
-    mac_rate = S * MACS_PER_STREAM_BLOCK / (sum(v for k, v in kernel_ms.items() if k != "pll" and k != "mix") * 1e-3) / 1e12
-    fp32 = {"fir_tmacs_per_s": round(mac_rate, 3), "peak_tmacs_per_s_no_fma": 31.1,
-            "peak_note": "148 SM x 111 MAC lanes/clk (packed FMUL2+FADD2 issue rate measured by tools/ubench.cu) x 1.9 GHz; "
-                         "a bit-exact MAC is one multiply and one add, never an FMA",
-            "frac": round(mac_rate / 31.1, 4), "pll_ns_per_step": round(kernel_ms.get("pll", 0) * 1e6 / n_if, 1)}
+    fir_ms = sum(v for k, v in kernel_ms.items() if k not in ("pll", "mix"))
+    mac_rate = S * MACS_PER_STREAM_BLOCK / (fir_ms * 1e-3) / 1e12
+    # no-FMA MAC issue peak: tools/ubench.cu measures 60.5 MAC lanes/clk/SM for FMUL+FADD (and the same for the packed
+    # FFMA2+FADD2 pair: packed instructions issue at half rate), i.e. half of the 128-lane FP32 pipe, x 148 SMs x max SM clock
+    sm_clock = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    peak_no_fma = 60.5 * 148 * sm_clock / 1e12
+    fp32 = {"fir_tmacs_per_s": round(mac_rate, 3), "peak_tmacs_per_s_no_fma": round(peak_no_fma, 2),
+            "peak_note": "60.5 MAC lanes/clk/SM measured for the unfused multiply+add (profiles/ubench_r1.txt) x 148 SMs x max SM clock; "
+                         "a bit-exact MAC is one multiply and one add, never an FMA, so this is half the FP32 FMA peak",
+            "frac": round(mac_rate / peak_no_fma, 4), "fir_kernels_ms": round(fir_ms, 4),
+            "per_kernel_frac": {k: round(S * m / (kernel_ms[k] * 1e-3) / 1e12 / peak_no_fma, 3)
+                                for k, m in (("rf_frontend", 1_484_700), ("if_bands", 2_227_050), ("rds_carrier_bpf", 742_350),
+                                             ("audio", 296_940), ("rds_backend", 572_872)) if k in kernel_ms},
+            "pll_ns_per_step": round(kernel_ms.get("pll", 0) * 1e6 / n_if, 1),
+            "pll_cycles_per_step": round(kernel_ms.get("pll", 0) * 1e-3 / n_if * sm_clock, 0),
+            "pll_chain_floor_cycles": 300,
+            "pll_note": "k_pll is bound by one dependent chain per sample (7350 sequential samples per block); the floor is that "
+                        "chain's length with the measured instruction latencies (DESIGN.md section 5)"}
 
     # ---- end to end through the host-facing call
     e2e = None

@@ -468,8 +468,15 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
 
     TRYCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
-    for (cudaStream_t* st : {&c->s_front, &c->s_pll, &c->s_back, &c->s_h2d, &c->s_d2h})
-        TRYCU(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+    {
+        // The PLL kernel needs whole SMs (it reserves their shared memory) and is the longest dependency chain of a step:
+        // its stream gets the highest priority so the block scheduler stops refilling SMs with FIR CTAs while PLL CTAs wait.
+        int prio_lo = 0, prio_hi = 0;
+        TRYCU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        for (cudaStream_t* st : {&c->s_front, &c->s_back, &c->s_h2d, &c->s_d2h})
+            TRYCU(cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio_lo));
+        TRYCU(cudaStreamCreateWithPriority(&c->s_pll, cudaStreamNonBlocking, prio_hi));
+    }
     for (cudaEvent_t* e : {&c->ev_in, &c->ev_join, &c->ev_h2d[0], &c->ev_h2d[1]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (int i = 0; i < kNRing; i++)
         for (cudaEvent_t* e : {&c->ev_front[i], &c->ev_pll[i], &c->ev_back[i]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
