@@ -292,8 +292,14 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes.get(dom, 0) / (kernel_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/), scaled to this batch
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = int(t["dram_bytes_per_launch"][dom] * S / t["streams"])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 5), "traffic": None,
+                "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "algorithmic_bytes": alg_bytes.get(dom, 0),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
                 "kernel_ms": {k: round(v, 4) for k, v in kernel_ms.items()},
                 "note": "the chain is FP32-issue / latency bound, not HBM bound (DESIGN.md section 5): see fp32"}
