@@ -189,6 +189,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line (rank 0): everything else that libraries print there (e.g. NCCL's version
+    # banner) is sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
     if args.impl == "reference":
         if rank != 0:
@@ -201,7 +208,7 @@ def main():
                 "cpu_baseline": {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": round(r["value"], 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -211,6 +218,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the receive chain has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = {}
+    try:  # NUMA-local pinned buffers: bind to the CPUs next to this GPU before anything is allocated
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        numa = load_mod("sdrb_shard", "real-time-sdr_b200/shard.py").bind_process_to_gpu_node(bus)
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     entry.build()
@@ -373,8 +387,9 @@ def main():
                 "config": {"workload": WORKLOAD.format(s=S), "mode": MODE, "type": KIND, "streams_per_gpu": S,
                            "l2": f"{N_INPUTS} distinct step inputs of {S * pitch / 1e6:.0f} MB cycled (each larger than the 126 MB L2)",
                            "realtime_factor": round(value / (world * S * 2.4), 2)},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu}
-        print(json.dumps(line))
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu,
+                "host": {"numa_binding_rank0": numa, "cpus": os.cpu_count()}}
+        emit(line)
     ch.close()
     if world > 1:
         dist.destroy_process_group()
