@@ -127,6 +127,29 @@ SDRB_HD dd dd_div(dd a, dd b) {
     return dd_add_d(q, q3);
 }
 
+// ---- full-precision constants of the hot path ----
+// A 64-bit floating-point immediate does not exist in SASS: written as literals, these constants are rebuilt with two
+// register moves each, in every step of the PLL recurrence (a sixth of its instruction stream).  On the device they
+// live in constant memory instead, where DFMA/DMUL/DADD read them as operands; the host build uses the same table.
+#define SDRB_PLL_CONSTS                                                                                         \
+    {8.33333333332248946124e-03, -1.66666666666666324348e-01, 2.75573137070700676789e-06, -1.98412698298579493134e-04, \
+     1.58969099521155010221e-10, -2.50507602534068634195e-08, -1.38888888888741095749e-03, 4.16666666666666019037e-02, \
+     -2.75573143513906633035e-07, 2.48015872894767294178e-05, -1.13596475577881948265e-11, 2.08757232129817482790e-09, \
+     0x1.45f306dc9c883p-1, 0x1.1846980000000p-44, 0x1.3198a2e037073p-69, 536870913.0, 0x1.1a62633145c07p-54,     \
+     0x1.921fb54442d18p+0}
+enum PllConst { kS2, kS1, kS4, kS3, kS6, kS5, kC2, kC1, kC4, kC3, kC6, kC5, kK2OverPi, kKP3, kKP4Rest, kKSplit, kKPio2M, kKPio2H };
+#if defined(__CUDACC__)
+__device__ __constant__ double c_pll_consts[18] = SDRB_PLL_CONSTS;
+#endif
+static const double h_pll_consts[18] = SDRB_PLL_CONSTS;
+SDRB_HD double K(PllConst i) {
+#if defined(__CUDA_ARCH__)
+    return c_pll_consts[i];
+#else
+    return h_pll_consts[i];
+#endif
+}
+
 // ---- float rounding boundary test ----
 // A double v rounds to float by dropping its low 29 mantissa bits; the boundary (tie) pattern of those
 // bits is 0x10000000.  `true` means: v is so close to a boundary (or so small that the float is
@@ -170,15 +193,15 @@ SDRB_HD void sincos_poly(double r, double& sr, double& cr_) {
     const double z = dmul(r, r);
     const double z2 = dmul(z, z), z4 = dmul(z2, z2);
     // sin r = r + r z (S1 + S2 z + S3 z^2 + S4 z^3 + S5 z^4 + S6 z^5)
-    const double s12 = dfma(8.33333333332248946124e-03, z, -1.66666666666666324348e-01);
-    const double s34 = dfma(2.75573137070700676789e-06, z, -1.98412698298579493134e-04);
-    const double s56 = dfma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08);
+    const double s12 = dfma(K(kS2), z, K(kS1));
+    const double s34 = dfma(K(kS4), z, K(kS3));
+    const double s56 = dfma(K(kS6), z, K(kS5));
     const double sp = dfma(z4, s56, dfma(z2, s34, s12));
     sr = dfma(dmul(r, z), sp, r);
     // cos r = 1 - z/2 + z^2 (C1 + C2 z + C3 z^2 + C4 z^3 + C5 z^4 + C6 z^5)
-    const double c12 = dfma(-1.38888888888741095749e-03, z, 4.16666666666666019037e-02);
-    const double c34 = dfma(-2.75573143513906633035e-07, z, 2.48015872894767294178e-05);
-    const double c56 = dfma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09);
+    const double c12 = dfma(K(kC2), z, K(kC1));
+    const double c34 = dfma(K(kC4), z, K(kC3));
+    const double c56 = dfma(K(kC6), z, K(kC5));
     const double cp = dfma(z4, c56, dfma(z2, c34, c12));
     cr_ = dfma(z2, cp, dfma(-0.5, z, 1.0));
 }
@@ -546,10 +569,10 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     const double m2 = f.r > 0.0 ? 2.0 : -2.0;
     const double m13 = (m & 2) ? 1.0 : -1.0;
     const double mm = (m & 1) ? m13 : ((m & 2) ? m2 : 0.0);
-    const double base = dadd(dmul(mm, kPio2H), -f.r);
+    const double base = dadd(dmul(mm, K(kKPio2H)), -f.r);
     const double u = dfma((double)y, f.c0, dmul((double)x, f.s0));
     const double w = dmul(u, rin);
-    const double e = dadd(base, dfma(mm, kPio2M, w));
+    const double e = dadd(base, dfma(mm, K(kKPio2M), w));
     bad |= (unsigned)(x == 0.0f) | (unsigned)(y == 0.0f) | (unsigned)!(fabs(w) < 0x1p-22) | (unsigned)!(fabs(e) < 3.14159) |
            ambig_abs(e);
     const float errorD = (float)e;
@@ -560,18 +583,18 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     const float trigArg = (float)td;
     // (double)trigArg without the float round trip: Veltkamp's split rounds td to 24 significant bits (to nearest);
     // an exact tie could round the other way, so ties and anything outside the float-normal range count as bad.
-    const double vt = dmul(td, 536870913.0);  // 2^29 + 1
+    const double vt = dmul(td, K(kKSplit));  // 2^29 + 1
     const double xd = dadd(vt, -dadd(vt, -td));
     bad |= (unsigned)!(fabs(td) < kReduceLimit) | (unsigned)!(fabs(td) > 0x1p-100) |
            (unsigned)(((uint32_t)dbits(td) & 0x1FFFFFFFu) == 0x10000000u);
     // quarter-turn reduction and polynomials (sincos_reduced, inlined so that its test joins `bad`).  The quadrant
     // count only needs x approximately, so it is taken from td and runs beside the split above, not after it; where
     // td and xd would round to different k the reduced argument merely ends a hair outside pi/4.
-    const double tm = dfma(td, kTwoOverPi, kMagicRint);
+    const double tm = dfma(td, K(kK2OverPi), kMagicRint);
     const double kd = dadd(tm, -kMagicRint);
     const int q = (int)(uint32_t)dbits(tm) & 3;
     double r = dfma(-kd, kP2, dfma(-kd, kP1, xd));
-    r = dadd(r, -dfma(kd, kP3, dmul(kd, kP4Rest)));
+    r = dadd(r, -dfma(kd, K(kKP3), dmul(kd, K(kKP4Rest))));
     double sr, cr_, ds, dc;
     sincos_poly(r, sr, cr_);
     sincos_quadrant(q, sr, cr_, ds, dc);
