@@ -1074,8 +1074,8 @@ __global__ void k_state_update(const float* x, size_t x_pitch, int nx, float* st
     if (i >= nstate) return;
     float* ss = state + (size_t)s * nstate;
     const float* xs = x + (size_t)s * x_pitch;
-    // nx >= nstate at every reference call site; otherwise the old state slides (done out of place by
-    // the caller passing nx < nstate is rejected on the host side)
+    // nx >= nstate at every reference call site; the host entry points reject shorter inputs (the reference reads
+    // out of bounds there)
     ss[i] = xs[nx - nstate + i];
 }
 
