@@ -223,3 +223,27 @@ def test_full_size_batch_1024_streams(capi, oracle, station_iq):
         if not np.array_equal(all_pcm[:, s, :].reshape(-1), w["pcm"]) or not np.array_equal(got_bits, w["rds_bits"]):
             bad.append(s)
     assert not bad, f"{len(bad)} of {S} streams differ from their oracle run, first: {bad[:8]}"
+
+
+def test_state_save_load_in_overlap_mode_single_stream(capi, oracle, station_iq):
+    """Checkpoint taken while the pipeline is in flight (overlap mode, one stream): the resumed run continues bit-exactly."""
+    nblocks, cut = 20, 9
+    iq = station_iq(4, 0, nblocks)
+    want = oracle.chain(0, "s", iq)
+    pcm = []
+    with capi.Chain(0, "s", n_streams=1) as a:
+        a.set_overlap(True)
+        bb = a.info.block_bytes
+        for b in range(cut):
+            a.process_host(iq[b * bb:(b + 1) * bb].reshape(1, bb))
+            pcm.append(a.read_pcm()[0].copy())
+        a.process_host(iq[cut * bb:(cut + 1) * bb].reshape(1, bb))  # in flight when the state is taken
+        blob = a.state_save()
+        pcm.append(a.read_pcm()[0].copy())
+    with capi.Chain(0, "s", n_streams=1) as c2:
+        c2.set_overlap(True)
+        c2.state_load(blob)
+        for b in range(cut + 1, nblocks):
+            c2.process_host(iq[b * bb:(b + 1) * bb].reshape(1, bb))
+            pcm.append(c2.read_pcm()[0].copy())
+    assert np.array_equal(np.concatenate(pcm), want["pcm"])
