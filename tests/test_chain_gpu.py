@@ -247,3 +247,28 @@ def test_state_save_load_in_overlap_mode_single_stream(capi, oracle, station_iq)
             c2.process_host(iq[b * bb:(b + 1) * bb].reshape(1, bb))
             pcm.append(c2.read_pcm()[0].copy())
     assert np.array_equal(np.concatenate(pcm), want["pcm"])
+
+
+@pytest.mark.parametrize("mode,kind,nblocks,S", [(2, "s", 4, 5), (1, "s", 5, 7), (3, "m", 5, 40), (2, "m", 4, 33)])
+def test_other_modes_batched(capi, oracle, station_iq, mode, kind, nblocks, S):
+    """Modes 1-3 (other front-end decimations, 147/800 and 147/1280 audio resamplers) as ragged batches, overlap mode."""
+    iqs = [station_iq(k % 3, mode, nblocks) for k in range(S)]
+    wants = [oracle.chain(mode, kind, station_iq(k, mode, nblocks)) for k in range(3)]
+    got = run_cuda_chain(capi, mode, kind, iqs, nblocks, overlap=True)
+    for s in range(S):
+        assert np.array_equal(got[s]["pcm"], wants[s % 3]["pcm"]), (mode, kind, s)
+
+
+def test_argument_checks(capi):
+    torch = pytest.importorskip("torch")
+    with capi.Chain(0, "m", 2) as ch:
+        buf = torch.zeros((2, ch.info.block_bytes + 16), dtype=torch.uint8, device="cuda")
+        with pytest.raises(capi.SdrError):
+            ch.process_device(buf.data_ptr() + 1, ch.info.block_bytes + 16)   # odd address
+        with pytest.raises(capi.SdrError):
+            ch.process_device(buf.data_ptr(), ch.info.block_bytes + 1)        # odd pitch
+        with pytest.raises(capi.SdrError):
+            ch.read_results(2, None, None)                                     # lag out of range
+        ch.process_device(buf.data_ptr() + 2, ch.info.block_bytes + 16)       # 2-byte aligned, not 16: plain-load path
+        ch.sync()
+        assert ch.read_pcm().shape == (2, 1470)
