@@ -88,14 +88,25 @@ def cpu_reference_run(nblocks=98, steps=1, warmup=0):
                 p.wait()
             return time.perf_counter() - t0
 
+        single = None
         try:
             for _ in range(warmup):
                 one_round()
             times = [one_round() for _ in range(max(1, steps))]
+            # the same reference functions on ONE thread (the function-level harness of oracle/): MS/s per core
+            harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+            if os.path.exists(harness):
+                out = path + ".rec"
+                t0 = time.perf_counter()
+                subprocess.run([harness, "chain", "0", "r", path, out, "-1", "out"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                single = pairs / (time.perf_counter() - t0) / 1e6
+                if os.path.exists(out):
+                    os.unlink(out)
         finally:
             os.unlink(path)
         dt = statistics.median(times)
         return {"value": inst * pairs / dt / 1e6, "unit": UNIT, "cores": min(cores, 3 * inst), "kind": "reference",
+                "single_thread": None if single is None else round(single, 2),
                 "sample": f"{inst} concurrent instance(s) of oracle/_ref/project 0 r (3 threads each), {nblocks + 3} blocks "
                           f"({pairs / 2.4e6:.1f} s of signal) of synthetic station 0 per instance, median of {len(times)}",
                 "ms_per_step": dt * 1e3}
@@ -205,7 +216,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD.format(s=args.streams), "mode": MODE, "type": KIND},
-                "cpu_baseline": {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                "cpu_baseline": {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                 "single_thread_ms_per_s": r.get("single_thread")},
                 "e2e": {"value": round(r["value"], 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -378,7 +390,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(nblocks=98, steps=3, warmup=0)
-        cpu = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        cpu = {"value": round(r["value"], 3), "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "single_thread_ms_per_s": r.get("single_thread")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
