@@ -547,18 +547,18 @@ SDRB_HD float pll_step_fast(float in, double rin, PllFast& f, const PllCoef& k, 
 // ~1e-5 per step) case that any test failed restores the state it saved and repeats those steps with pll_step_fast.
 SDRB_HD unsigned ambig_rel(double v) {  // near_float_boundary, branch-free (also flags zero / float-subnormal)
     const uint64_t b = dbits(v);
-    const uint32_t e = (uint32_t)(b >> 52) & 0x7FFu;
-    const uint32_t low = (uint32_t)b & 0x1FFFFFFFu;
-    const uint32_t dist = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
-    return (unsigned)(dist <= kAmbigUlps) | (unsigned)(e < 1023u - 126u + 1u);
+    const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    // |low29 - 0x10000000| <= T  <=>  (low29 - (0x10000000 - T)) <= 2T as unsigned (one subtract, one compare)
+    const uint32_t off = (lo & 0x1FFFFFFFu) - (0x10000000u - kAmbigUlps);
+    return (unsigned)(off <= 2u * kAmbigUlps) | (unsigned)((hi & 0x7FF00000u) < ((1023u - 126u + 1u) << 20));
 }
 SDRB_HD unsigned ambig_abs(double v) {  // near_float_boundary_abs, branch-free
     const uint64_t b = dbits(v);
-    const int e = (int)((b >> 52) & 0x7FFu) - 1023;
-    const uint32_t low = (uint32_t)b & 0x1FFFFFFFu;
-    const uint32_t dist = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
-    const uint32_t thr = 1u << ((52 + kAtanTolLog2 - e) & 31);
-    return (unsigned)(e < -17) | (unsigned)(e > 1) | (unsigned)(dist <= thr);
+    const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    const uint32_t E = (hi >> 20) & 0x7FFu;                      // biased exponent; accepted range e in [-17, 1]
+    const uint32_t thr = 1u << ((1023u + 52u + (uint32_t)kAtanTolLog2 - E) & 31u);  // tolerance in units of 2^(e-52)
+    const uint32_t off = (lo & 0x1FFFFFFFu) - 0x10000000u + thr;
+    return (unsigned)((E - (1023u - 17u)) > 18u) | (unsigned)(off <= 2u * thr);
 }
 
 SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, unsigned& bad) {
