@@ -592,7 +592,11 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     // td and xd would round to different k the reduced argument merely ends a hair outside pi/4.
     const double tm = dfma(td, K(kK2OverPi), kMagicRint);
     const double kd = dadd(tm, -kMagicRint);
+#if defined(__CUDA_ARCH__)
+    const int q = __double2loint(tm) & 3;  // 32-bit all the way (the 64-bit route costs extra compare halves)
+#else
     const int q = (int)(uint32_t)dbits(tm) & 3;
+#endif
     double r = dfma(-kd, kP2, dfma(-kd, kP1, xd));
     r = dadd(r, -dfma(kd, K(kKP3), dmul(kd, K(kKP4Rest))));
     double sr, cr_, ds, dc;

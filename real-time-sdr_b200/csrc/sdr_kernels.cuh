@@ -462,12 +462,13 @@ struct PllArgs {
 
 constexpr int kPllThreads = 128;  // four warps = one per SM sub-partition: each has a scheduler (and FP64 lanes) to itself
 
-// 1/(double)v to ~2^-40 relative (MUFU.RCP64H seed + one Newton step); v = 0 or subnormal gives inf/NaN, which
-// the caller's |w| test turns into the general path.  Only ~2^-25 is needed (see pll_step_fast).
+// 1/v for the rotated phase detector: w = u * (1/in) is a <= 2^-22 rad correction whose absolute error may be 2^-45,
+// so a relative 2^-23 is enough: the FP32 reciprocal approximation (MUFU.RCP, 1 ulp) widened to double.  v = 0 or
+// subnormal gives inf, which the step's |w| test turns into the general path.
 __device__ __forceinline__ double pll_recip(float v) {
-    double d = (double)v, r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    return __fma_rn(r, __fma_rn(-d, r, 1.0), r);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return (double)r;
 }
 
 constexpr int kPllTileChunks = 8;  // 32 steps per staged tile
