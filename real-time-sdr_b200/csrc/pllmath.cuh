@@ -573,8 +573,11 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     const double u = dfma((double)y, f.c0, dmul((double)x, f.s0));
     const double w = dmul(u, rin);
     const double e = dadd(base, dfma(mm, K(kKPio2M), w));
-    bad |= (unsigned)(x == 0.0f) | (unsigned)(y == 0.0f) | (unsigned)!(fabs(w) < 0x1p-22) | (unsigned)!(fabs(e) < 3.14159) |
-           ambig_abs(e);
+    // Zero products need no test of their own: in = 0 (or subnormal, flushed by the caller's reciprocal) makes rin
+    // infinite and w NaN/inf, which fails |w| < 2^-22; y = 0 alone puts e at ~0 or ~+-pi, both rejected below; x = 0
+    // alone (an underflowed in*cos) is an ordinary small perturbation; both zero with a normal `in` cannot happen
+    // because max(|cos|, |sin|) >= 0.7.
+    bad |= (unsigned)!(fabs(w) < 0x1p-22) | (unsigned)!(fabs(e) < 3.14159) | ambig_abs(e);
     const float errorD = (float)e;
     f.integ = fadd(f.integ, fmul(k.Ki, errorD));
     f.phase = fadd(fadd(f.phase, fmul(k.Kp, errorD)), f.integ);

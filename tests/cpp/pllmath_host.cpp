@@ -128,7 +128,8 @@ void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, flo
     int i = 0;
     for (; i + 4 <= n; i += 4) {  // the kernel's chunking: 4 speculative steps, verified once
         float c[4] = {in[i], in[i + 1], in[i + 2], in[i + 3]}, th[4];
-        double r[4] = {1.0 / (double)c[0], 1.0 / (double)c[1], 1.0 / (double)c[2], 1.0 / (double)c[3]};
+        auto recip = [](float v) { return (fabsf(v) < 1.17549435e-38f) ? (double)INFINITY : 1.0 / (double)v; };  // device: rcp.approx.ftz
+        double r[4] = {recip(c[0]), recip(c[1]), recip(c[2]), recip(c[3])};
         PllFast probe = f;
         unsigned bad = f.generic_next ? 1u : 0u;
         for (int j = 0; j < 4; j++) pll_step_spec(c[j], r[j], probe, k, bad);
