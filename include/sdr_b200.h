@@ -187,7 +187,8 @@ size_t sdrb_chain_state_bytes(const sdrb_chain* c);
 int sdrb_chain_state_save(sdrb_chain* c, void* h_blob);
 int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob);
 
-/* Device time of the kernels of the most recent block, by kernel family, in milliseconds (CUDA events).
+/* Mean device time per launch of each kernel family, in milliseconds, over the blocks processed since profiling was
+ * switched on (CUDA event pairs recorded on the stream each kernel runs on; at most the last 128 blocks).
  * names/ms arrays of capacity cap; returns the count in *n. */
 int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int cap, int* n);
 int sdrb_chain_set_profiling(sdrb_chain* c, int on);

@@ -57,10 +57,13 @@ struct Ring {
     const float* cur(long long b) const { return base + (size_t)(b % kNRing) * slot + halo; }
 };
 
+// Per-kernel-family device timing: a ring of CUDA event pairs, one pair per launch, recorded on the stream the kernel
+// runs on.  sdrb_chain_kernel_times reports the mean over the launches since profiling was switched on.
+constexpr int kTimedSlots = 128;
 struct Timed {
     const char* name;
-    cudaEvent_t e0, e1;
-    bool used;
+    std::vector<cudaEvent_t> e0, e1;
+    long long n;  // launches recorded since profiling was enabled
 };
 
 }  // namespace
@@ -129,9 +132,13 @@ void copy_taps(Taps101& t, const std::vector<float>& h) { memcpy(t.h, h.data(), 
 Timed* timer_for(sdrb_chain* c, const char* name) {
     for (auto& t : c->timed)
         if (strcmp(t.name, name) == 0) return &t;
-    Timed t{name, nullptr, nullptr, false};
-    cudaEventCreate(&t.e0);
-    cudaEventCreate(&t.e1);
+    Timed t{name, {}, {}, 0};
+    t.e0.resize(kTimedSlots);
+    t.e1.resize(kTimedSlots);
+    for (int i = 0; i < kTimedSlots; i++) {
+        cudaEventCreate(&t.e0[i]);
+        cudaEventCreate(&t.e1[i]);
+    }
     c->timed.push_back(t);
     return &c->timed.back();
 }
@@ -140,15 +147,17 @@ struct ScopedTimer {
     sdrb_chain* c;
     cudaStream_t st;
     Timed* t = nullptr;
+    int slot = 0;
     ScopedTimer(sdrb_chain* c_, const char* name, cudaStream_t st_) : c(c_), st(st_) {
         if (c->profiling) {
             t = timer_for(c, name);
-            t->used = true;
-            cudaEventRecord(t->e0, st);
+            slot = (int)(t->n % kTimedSlots);
+            t->n++;
+            cudaEventRecord(t->e0[slot], st);
         }
     }
     ~ScopedTimer() {
-        if (t) cudaEventRecord(t->e1, st);
+        if (t) cudaEventRecord(t->e1[slot], st);
     }
 };
 
@@ -401,10 +410,11 @@ int sdrb_chain_destroy(sdrb_chain* c) {
     for (int i = 0; i < kNRing; i++)
         for (cudaEvent_t e : {c->ev_front[i], c->ev_pll[i], c->ev_back[i]})
             if (e) cudaEventDestroy(e);
-    for (auto& t : c->timed) {
-        cudaEventDestroy(t.e0);
-        cudaEventDestroy(t.e1);
-    }
+    for (auto& t : c->timed)
+        for (int i = 0; i < kTimedSlots; i++) {
+            cudaEventDestroy(t.e0[i]);
+            cudaEventDestroy(t.e1[i]);
+        }
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return SDRB_OK;
@@ -873,6 +883,8 @@ int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob) {
 int sdrb_chain_set_profiling(sdrb_chain* c, int on) {
     if (!c) return fail(SDRB_ERR_INVALID, "null argument");
     c->profiling = on != 0;
+    if (c->profiling)
+        for (auto& t : c->timed) t.n = 0;  // a new measurement window
     return SDRB_OK;
 }
 
@@ -883,11 +895,16 @@ int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int ca
     CU(cudaStreamSynchronize(c->stream));
     int k = 0;
     for (auto& t : c->timed) {
-        if (!t.used || k >= cap) continue;
-        float v = 0;
-        CU(cudaEventElapsedTime(&v, t.e0, t.e1));
+        if (t.n == 0 || k >= cap) continue;
+        const int cnt = (int)(t.n < kTimedSlots ? t.n : kTimedSlots);
+        double sum = 0;
+        for (int i = 0; i < cnt; i++) {
+            float v = 0;
+            CU(cudaEventElapsedTime(&v, t.e0[i], t.e1[i]));
+            sum += v;
+        }
         names[k] = t.name;
-        ms[k] = v;
+        ms[k] = (float)(sum / cnt);
         k++;
     }
     *n = k;
