@@ -433,7 +433,20 @@ struct PllFast {
     double r;       // that phase reduced: theta = r + kq*pi/2 (mod 2 pi)
     int kq;
     bool generic_next;  // c0/s0/r/kq are not valid: use the general atan2 at the next step
+    double magic;       // 1.5 * 2^(E+29), E = binade of the current NCO phase: td + magic - magic rounds td to float precision
 };
+// 1.5 * 2^(E+29) for the binade E of v: adding it to a number of that binade leaves exactly 24 significant bits (RNE).
+SDRB_HD double float_round_magic(double v) {
+    const uint64_t b = dbits(v);
+    const uint64_t m = ((b & 0x7FF0000000000000ull) + (29ull << 52)) | (1ull << 51);
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)m);
+#else
+    double o;
+    memcpy(&o, &m, 8);
+    return o;
+#endif
+}
 constexpr double kMagicRint = 6755399441055744.0;  // 1.5 * 2^52: x + magic - magic = rint(x), integer in the low word
 constexpr int kAtanTolLog2 = -43;                  // absolute error bound of the rotated phase detector, see above
 
@@ -475,6 +488,7 @@ SDRB_HD float cos_lean_f(float t) {
 
 SDRB_HD void pll_fast_sincos(float trigArg, PllFast& f) {
     double x = (double)trigArg;
+    f.magic = float_round_magic(x);
     bool ok = fabs(x) < kReduceLimit && trigArg != 0.0f;
     if (ok) {
         double ds, dc, r;
@@ -584,16 +598,17 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     f.trigOffset = dadd(f.trigOffset, 1.0);
     const double td = dadd(dmul(k.w, f.trigOffset), (double)f.phase);
     const float trigArg = (float)td;
-    // (double)trigArg without the float round trip: Veltkamp's split rounds td to 24 significant bits (to nearest);
-    // an exact tie could round the other way, so ties and anything outside the float-normal range count as bad.
-    const double vt = dmul(td, K(kKSplit));  // 2^29 + 1
-    const double xd = dadd(vt, -dadd(vt, -td));
-    bad |= (unsigned)!(fabs(td) < kReduceLimit) | (unsigned)!(fabs(td) > 0x1p-100) |
-           (unsigned)(((uint32_t)dbits(td) & 0x1FFFFFFFu) == 0x10000000u);
+    // (double)trigArg without the float round trip: td + M - M with M = 1.5 * 2^(E+29) rounds td to 24 significant bits,
+    // to nearest even, exactly like the conversion, provided td lies in the binade E that M was built for.  M comes from
+    // the previous step's phase (the binade changes once per doubling of the phase); a mismatch counts as bad.
+    const double xd = dadd(dadd(td, f.magic), -f.magic);
+    const double magic_next = float_round_magic(td);
+    bad |= (unsigned)!(fabs(td) < kReduceLimit) | (unsigned)!(fabs(td) > 0x1p-100) | (unsigned)(magic_next != f.magic);
+    f.magic = magic_next;
     // quarter-turn reduction and polynomials (sincos_reduced, inlined so that its test joins `bad`).  The quadrant
-    // count only needs x approximately, so it is taken from td and runs beside the split above, not after it; where
-    // td and xd would round to different k the reduced argument merely ends a hair outside pi/4.
-    const double tm = dfma(td, K(kK2OverPi), kMagicRint);
+    // count must come from xd, not td: once the phase passes 2^22 the float grid is coarser than pi/4, td and xd can
+    // be a radian apart, and a count taken from td would leave |r| far outside the range of the kernels below.
+    const double tm = dfma(xd, K(kK2OverPi), kMagicRint);
     const double kd = dadd(tm, -kMagicRint);
 #if defined(__CUDA_ARCH__)
     const int q = __double2loint(tm) & 3;  // 32-bit all the way (the 64-bit route costs extra compare halves)

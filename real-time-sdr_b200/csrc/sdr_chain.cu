@@ -86,6 +86,7 @@ struct sdrb_chain {
     Taps101 rf_h, pilot_h, stereo_h, rds_h, rds114_h, rrc_h, audio_h;
     float* d_audio_pm = nullptr;   // phase-major audio taps (up > 1)
     float* d_rds_perm = nullptr;   // permuted RDS low-pass taps
+    int* d_rds_thread_phase = nullptr;
     // input
     uint8_t* d_iq[2] = {nullptr, nullptr};  // staging for process_host
     size_t iq_pitch = 0;
@@ -350,6 +351,7 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
         a.dc = c->rdc.cur(b); a.dc_pitch = c->rdc.pitch;
         a.n_in = n_if; a.n_out = c->info.rds_block; a.sps = 39; a.rds_on = c->cfg.rds_on;
         a.taps_perm = c->d_rds_perm;
+        a.thread_phase = c->d_rds_thread_phase;
         a.rrc = c->rrc_h;
         a.filt_state_in = c->d_filt_state[b & 1];
         a.filt_state_out = c->d_filt_state[(b + 1) & 1];
@@ -527,13 +529,25 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         const int nh = kTaps * kRdsUp;
         std::vector<float> lh(nh);
         sdrb_design_lpf_gain((float)(cfg->if_Fs * kRdsUp), 3e3f, nh, kRdsUp, lh.data());  // src/rds.cpp:61
+        // thread -> output residue: warp by warp, 32 residues whose input offsets floor(640 tp/247) differ modulo 32
+        std::vector<int> thread_phase(256, -1);
+        {
+            std::vector<std::vector<int>> by_bank(32);
+            for (int tp = 0; tp < kRdsUp; tp++) by_bank[((kRdsDown * tp) / kRdsUp) % 32].push_back(tp);
+            for (int b = 0; b < 32; b++)
+                for (size_t i = 0; i < by_bank[b].size(); i++) thread_phase[32 * i + b] = by_bank[b][i];  // at most 8 per bank
+        }
         std::vector<float> perm((size_t)kTaps * 256, 0.0f);
-        for (int t = 0; t < kRdsUp; t++) {
-            const int phase = (kRdsDown * t) % kRdsUp;
-            for (int j = 0; j < kTaps; j++) perm[(size_t)j * 256 + t] = lh[phase + kRdsUp * j];
+        for (int th = 0; th < 256; th++) {
+            const int tp = thread_phase[th];
+            if (tp < 0) continue;
+            const int phase = (kRdsDown * tp) % kRdsUp;
+            for (int j = 0; j < kTaps; j++) perm[(size_t)j * 256 + th] = lh[phase + kRdsUp * j];
         }
         TRY(dalloc(c, (void**)&c->d_rds_perm, perm.size() * sizeof(float)));
+        TRY(dalloc(c, (void**)&c->d_rds_thread_phase, 256 * sizeof(int)));
         TRYCU(cudaMemcpyAsync(c->d_rds_perm, perm.data(), perm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        TRYCU(cudaMemcpyAsync(c->d_rds_thread_phase, thread_phase.data(), 256 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         TRYCU(cudaStreamSynchronize(c->stream));
     }
 

@@ -774,7 +774,8 @@ struct RdsArgs {
     int n_out;             // n_in*247/640
     int sps;
     int rds_on;
-    const float* taps_perm;  // [kTaps][256]: taps_perm[j*256 + t] = h_lpf[(146*t % 247) + 247*j]  (t < 247)
+    const float* taps_perm;  // [kTaps][256]: taps_perm[j*256 + thread] = h_lpf[(640*tp % 247) + 247*j], tp = thread_phase[thread]
+    const int* thread_phase; // [256]: the output residue tp (n = tp mod 247) each thread owns, -1 = idle
     Taps101 rrc;
     float* filt_state_in;    // [n_streams][kState] last rds_filt samples of the previous block
     float* filt_state_out;
@@ -844,17 +845,20 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     __syncthreads();
 
     // ---- 247/640 resampler (/root/reference/src/filter.cpp:123-147, src/rds.cpp:130).
-    // Outputs n and n+247 share the polyphase branch, so thread t (< 247) owns n = t + 247 q and keeps
-    // its 101 branch taps h[phase + 247 j] in flight once per pass over q.
-    if (t < kRdsUp) {
-        const int base = (kRdsDown * t) / kRdsUp;  // (n*down - phase)/up for q = 0
-        for (int q0 = 0; q0 * kRdsUp + t < n_out; q0 += kResQ) {
+    // Outputs n and n+247 share the polyphase branch, so one thread owns n = tp + 247 q and keeps its 101 branch taps
+    // h[phase + 247 j] in flight once per pass over q.  Which tp a thread owns is a host-made permutation
+    // (thread_phase): the 32 lanes of a warp get input offsets floor(640 tp / 247) that are distinct modulo 32, so the
+    // one shared-memory load per MAC of this stage is bank-conflict free (in natural order it is 2.6-way conflicted).
+    const int tp = a.thread_phase[t];
+    if (tp >= 0) {
+        const int base = (kRdsDown * tp) / kRdsUp;  // (n*down - phase)/up for q = 0
+        for (int q0 = 0; q0 * kRdsUp + tp < n_out; q0 += kResQ) {
             float acc[kResQ];
             int off[kResQ];
 #pragma unroll
             for (int qq = 0; qq < kResQ; qq++) {
                 acc[qq] = 0.0f;
-                int n = (q0 + qq) * kRdsUp + t;
+                int n = (q0 + qq) * kRdsUp + tp;
                 off[qq] = (n < n_out) ? kRdsDown * (q0 + qq) + base + kState : kState;
             }
             for (int j = 0; j < kTaps; j++) {
@@ -864,7 +868,7 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
             }
 #pragma unroll
             for (int qq = 0; qq < kResQ; qq++) {
-                int n = (q0 + qq) * kRdsUp + t;
+                int n = (q0 + qq) * kRdsUp + tp;
                 if (n < n_out) {
                     sfilt[pad_pos<kRrcR>(n + kState)] = acc[qq];
                     if (a.filt_out) a.filt_out[(size_t)s * n_out + n] = acc[qq];

@@ -156,3 +156,44 @@ def test_lean_cosine_equals_glibc(host):
     c = np.zeros_like(t)
     host.crh_cos_lean(t, t.size, c)
     assert np.array_equal(c.view(np.uint32), np.cos(t.astype(np.float64)).astype(np.float32).view(np.uint32))
+
+
+@pytest.mark.parametrize("freq,scale,bw", [(19e3, 2.0, 0.01), (114e3, 0.5, 0.001)])
+@pytest.mark.parametrize("n0", [2.0e6, 9.0e6, 4.0e7, 3.0e8])
+def test_fast_recurrence_at_large_phase(host, oracle, oracle_mod, freq, scale, bw, n0):
+    """Hours into a run the NCO phase is a float with an ulp of radians (2^22 rad is reached after 35 s / 6 s).  Start both
+    recurrences from the same state far down the road: the float grid is then coarser than a quadrant, which is exactly
+    where a reduction that is only approximately consistent goes wrong without the loop visibly losing lock."""
+    host.crh_pll_fast.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, f32p, f32p,
+                                  C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    n, nb = 7350, 3
+    t = np.arange(n * nb, dtype=np.float64) + n0
+    rng = np.random.default_rng(int(n0) % 1000)
+    x = (0.05 * np.cos(2 * np.pi * (freq + 2.0) / 240000.0 * t + 0.4) + 0.004 * rng.standard_normal(t.size)).astype(np.float32)
+    # oracle from a hand-made state at sample count n0 (feedback consistent with the phase, as fmpll leaves it)
+    st = oracle_mod.PllState()
+    oracle.lib.orc_pll_init(C.byref(st))
+    st.trigOffset = float(n0)
+    st.phaseEst = np.float32(0.37)
+    st.integrator = np.float32(1e-4)
+    th = np.float32(2 * np.pi * float(np.float32(freq) / np.float32(240000.0)) * n0 + float(st.phaseEst))
+    st.feedbackI = np.float32(np.cos(np.float64(th)))
+    st.feedbackQ = np.float32(np.sin(np.float64(th)))
+    want = []
+    out_o = np.zeros(n + 1, np.float32)
+    out_o[n] = 1
+    out_f = out_o.copy()
+    st4 = np.array([st.feedbackI, st.feedbackQ, st.integrator, st.phaseEst], np.float32)
+    trig = C.c_double(float(n0))
+    stats = (C.c_uint64 * 2)()
+    got = []
+    for b in range(nb):
+        xb = np.ascontiguousarray(x[b * n:(b + 1) * n])
+        oracle.lib.orc_pll(xb, n, freq, 240000.0, out_o, C.byref(st), scale, 0.0, bw)
+        host.crh_pll_fast(xb, n, freq, 240000.0, scale, 0.0, bw, out_f, st4, C.byref(trig), stats)
+        want.append(out_o.copy())
+        got.append(out_f.copy())
+    want, got = np.concatenate(want), np.concatenate(got)
+    assert int((want.view(np.uint32) != got.view(np.uint32)).sum()) == 0
+    assert [float(st.feedbackI), float(st.feedbackQ), float(st.integrator), float(st.phaseEst)] == [float(v) for v in st4]
+    assert st.trigOffset == trig.value
