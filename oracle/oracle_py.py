@@ -97,6 +97,7 @@ class Oracle:
         L.orc_chain_groups.restype = C.c_int
         L.orc_chain_text.argtypes = [C.c_void_p]
         L.orc_chain_text.restype = C.c_char_p
+        L.orc_chain_set_pll_sample_count.argtypes = [C.c_void_p, C.c_double]
         L.orc_run_batch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_run_batch.restype = C.c_int
 
@@ -213,10 +214,13 @@ class Oracle:
         return text.value.decode("latin-1")
 
     # ---- whole chain
-    def chain(self, mode: int, kind: str, iq: np.ndarray, stages=(), with_rds_dsp=False, max_blocks=None) -> dict:
+    def chain(self, mode: int, kind: str, iq: np.ndarray, stages=(), with_rds_dsp=False, max_blocks=None,
+              pll_sample_count: float | None = None) -> dict:
         """Run one stream; returns the same record names as RefHarness.chain()."""
         L = self.lib
         c = L.orc_chain_create(mode, ord(kind), 1 if (with_rds_dsp or "rds_clean" in stages) else 0)
+        if pll_sample_count is not None:
+            L.orc_chain_set_pll_sample_count(c, float(pll_sample_count))
         info = ChainInfo()
         L.orc_chain_get_info(c, C.byref(info))
         iq = np.ascontiguousarray(iq, np.uint8)

@@ -615,6 +615,18 @@ int orc_chain_groups(const orc_chain* c, const uint64_t** groups) {
 
 const char* orc_chain_text(const orc_chain* c) { return c->text; }
 
+static void orc_pll_jump(orc_pll_state* st, float freq, float Fs, double n0) {
+    st->trigOffset = n0;
+    float trigArg = (float)(2 * ORC_PI * (freq / Fs) * (st->trigOffset) + st->phaseEst); /* src/pll.cpp:47 */
+    st->feedbackI = (float)cos(trigArg);
+    st->feedbackQ = (float)sin(trigArg);
+}
+
+void orc_chain_set_pll_sample_count(orc_chain* c, double n0) {
+    orc_pll_jump(&c->pll19, 19e3f, (float)(c->rf_Fs / c->rf_decim), n0);
+    orc_pll_jump(&c->pll114, 114e3f, (float)c->if_Fs, n0);
+}
+
 /* ---- multi-threaded batch runner (CPU baseline only) ---- */
 typedef struct {
     int mode, type, nstreams, nblocks, tid, nthreads;

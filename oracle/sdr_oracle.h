@@ -102,6 +102,11 @@ int orc_chain_groups(const orc_chain* c, const uint64_t** groups);
 /* all stderr text so far */
 const char* orc_chain_text(const orc_chain* c);
 
+/* Test hook: puts both PLLs of the chain at sample count n0 (trigOffset = n0, feedbackI/Q = cos/sin of the phase that
+ * src/pll.cpp:47 gives for the carried phaseEst), as if n0 samples had already gone through.  Lets a short test reach the
+ * regime hours into a run where the float NCO phase has an ulp of radians. */
+void orc_chain_set_pll_sample_count(orc_chain* c, double n0);
+
 /* Run `nstreams` independent chains over `nblocks` blocks each on `nthreads` host threads (CPU baseline).
  * iq: [nstreams][nblocks*2*block_pairs]; pcm (may be NULL): [nstreams][nblocks*pcm_per_block];
  * groups_out (may be NULL): [nstreams] group counts.  Returns 0. */

@@ -272,3 +272,44 @@ def test_argument_checks(capi):
         ch.process_device(buf.data_ptr() + 2, ch.info.block_bytes + 16)       # 2-byte aligned, not 16: plain-load path
         ch.sync()
         assert ch.read_pcm().shape == (2, 1470)
+
+
+def _patch_pll_sample_count(capi, blob: bytes, S: int, n0: float) -> bytes:
+    """Rewrites both PLL states inside a state blob (layout of sdrb_chain_state_save for a mode-0 'r' chain: header, IQ halo,
+    ring halos fm 160 / rds_band 160 / trig19 4 / trig114 4 / stereo_dc 112 / rds_dc 112 floats, then the two PLL state arrays)."""
+    import struct
+    off = 24 + S * 224 + S * 4 * (160 + 160 + 4 + 4 + 112 + 112)
+    out = bytearray(blob)
+    for which, freq in ((0, 19e3), (1, 114e3)):
+        for s in range(S):
+            o = off + (which * S + s) * 24
+            fbI, fbQ, integ, phase, trig = struct.unpack_from("<4fd", out, o)
+            assert (fbI, fbQ, integ, phase, trig) == (1.0, 0.0, 0.0, 0.0, 0.0), "blob layout changed: fresh PLL state expected here"
+            th = np.float32(2 * np.pi * float(np.float32(freq) / np.float32(240000.0)) * n0 + phase)
+            struct.pack_into("<4fd", out, o, float(np.float32(np.cos(np.float64(th)))), float(np.float32(np.sin(np.float64(th)))),
+                             integ, phase, float(n0))
+    return bytes(out)
+
+
+@pytest.mark.parametrize("n0", [3.0e6, 2.0e7, 4.0e8])
+def test_chain_at_large_nco_phase(capi, oracle, station_iq, n0):
+    """The batched PLL kernel hours into a run: both loops are placed at sample count n0 through the checkpoint interface
+    (the oracle through its test hook), where the float NCO phase has an ulp of up to 64 rad.  Everything downstream of the
+    PLLs (carrier, IPLL, audio, RDS samples) must still be bit-identical."""
+    nblocks, S = 10, 2
+    iq = station_iq(0, 0, nblocks)
+    stages = ["carrier", "IPLL", "stereo_filt", "rds_clean"]
+    want = oracle.chain(0, "r", iq, stages=stages, pll_sample_count=n0)
+    acc = {k: [] for k in stages}
+    pcm = []
+    with capi.Chain(0, "r", n_streams=S, keep_stages=True) as ch:
+        ch.state_load(_patch_pll_sample_count(capi, ch.state_save(), S, n0))
+        bb = ch.info.block_bytes
+        for b in range(nblocks):
+            ch.process_host(np.stack([iq[b * bb:(b + 1) * bb]] * S))
+            pcm.append(ch.read_pcm()[1].copy())
+            for k in stages:
+                acc[k].append(ch.stage(k)[1])
+    got = {k: np.concatenate(v) for k, v in acc.items()}
+    got["pcm"] = np.concatenate(pcm)
+    _assert_same(got, want, ["pcm"] + stages, f"n0={n0}")
