@@ -135,13 +135,12 @@ SDRB_HD dd dd_div(dd a, dd b) {
     {8.33333333332248946124e-03, -1.66666666666666324348e-01, 2.75573137070700676789e-06, -1.98412698298579493134e-04, \
      1.58969099521155010221e-10, -2.50507602534068634195e-08, -1.38888888888741095749e-03, 4.16666666666666019037e-02, \
      -2.75573143513906633035e-07, 2.48015872894767294178e-05, -1.13596475577881948265e-11, 2.08757232129817482790e-09, \
-     0x1.45f306dc9c883p-1, 0x1.1846980000000p-44, 0x1.3198a2e037073p-69, 536870913.0, 0x1.1a62633145c07p-54,     \
-     0x1.921fb54442d18p+0}
-enum PllConst { kS2, kS1, kS4, kS3, kS6, kS5, kC2, kC1, kC4, kC3, kC6, kC5, kK2OverPi, kKP3, kKP4Rest, kKSplit, kKPio2M, kKPio2H };
+     0x1.45f306dc9c883p-1, 0x1.1a62633145c07p-54, 0x1.921fb54442d18p+0}
+enum PllConst { kS2, kS1, kS4, kS3, kS6, kS5, kC2, kC1, kC4, kC3, kC6, kC5, kK2OverPi, kKPio2M, kKPio2H };
 #if defined(__CUDACC__)
-__device__ __constant__ double c_pll_consts[18] = SDRB_PLL_CONSTS;
+__device__ __constant__ double c_pll_consts[15] = SDRB_PLL_CONSTS;
 #endif
-static const double h_pll_consts[18] = SDRB_PLL_CONSTS;
+static const double h_pll_consts[15] = SDRB_PLL_CONSTS;
 SDRB_HD double K(PllConst i) {
 #if defined(__CUDA_ARCH__)
     return c_pll_consts[i];
@@ -189,7 +188,7 @@ constexpr double kReduceLimit = 3.0e9;  // |x| below this: k < 2^31, exact Cody-
 // sin r and cos r for |r| <= pi/4: the degree-13 / degree-12 minimax kernels of fdlibm (k_sin.c, k_cos.c: S1..S6,
 // C1..C6, approximation error below 2^-58), evaluated Estrin-style so the dependent depth is z, z^2, z^4 and two fmas.
 // Far inside the 2^-45 the callers allow before they consult the double-double tier.
-SDRB_HD void sincos_poly(double r, double& sr, double& cr_) {
+SDRB_HD void sincos_poly2(double r, double rs, double& sr, double& cr_) {  // sr = sin(rs), rs = r or |r|
     const double z = dmul(r, r);
     const double z2 = dmul(z, z), z4 = dmul(z2, z2);
     // sin r = r + r z (S1 + S2 z + S3 z^2 + S4 z^3 + S5 z^4 + S6 z^5)
@@ -197,7 +196,7 @@ SDRB_HD void sincos_poly(double r, double& sr, double& cr_) {
     const double s34 = dfma(K(kS4), z, K(kS3));
     const double s56 = dfma(K(kS6), z, K(kS5));
     const double sp = dfma(z4, s56, dfma(z2, s34, s12));
-    sr = dfma(dmul(r, z), sp, r);
+    sr = dfma(dmul(rs, z), sp, rs);
     // cos r = 1 - z/2 + z^2 (C1 + C2 z + C3 z^2 + C4 z^3 + C5 z^4 + C6 z^5)
     const double c12 = dfma(K(kC2), z, K(kC1));
     const double c34 = dfma(K(kC4), z, K(kC3));
@@ -205,6 +204,7 @@ SDRB_HD void sincos_poly(double r, double& sr, double& cr_) {
     const double cp = dfma(z4, c56, dfma(z2, c34, c12));
     cr_ = dfma(z2, cp, dfma(-0.5, z, 1.0));
 }
+SDRB_HD void sincos_poly(double r, double& sr, double& cr_) { sincos_poly2(r, r, sr, cr_); }
 SDRB_HD double flip_sign_if(double v, unsigned flip) {  // exact negation by a sign-bit XOR (one integer op on the chain)
 #if defined(__CUDA_ARCH__)
     return __hiloint2double(__double2hiint(v) ^ (int)(flip << 31), __double2loint(v));
@@ -426,29 +426,87 @@ SDRB_HD float pll_step(float in, PllState& st, const PllCoef& k, const AtanTab& 
 // That replaces a table-driven atan2 with a double division by two multiplies and three adds.  The result
 // is accepted only if it is farther than kAtanAbsTol from a float rounding boundary, otherwise (and for
 // zero / subnormal / inconsistent inputs) the general correctly-rounded atan2_f above decides.
+//
+// State between steps: theta = r + kq*pi/2 (mod 2 pi) with |r| <= pi/4, and sa = |sin r|, cr = cos r in double.
+// sin/cos(theta) are +-sa / +-cr in an order and with signs that depend on kq and the sign of r only.
 struct PllFast {
     float fbI, fbQ, integ, phase;  // pllblock_args fields (/root/reference/include/pll.h:10-17)
     double trigOffset;
-    double c0, s0;  // cos/sin of the current NCO phase in double (fbI/fbQ are their float roundings)
-    double r;       // that phase reduced: theta = r + kq*pi/2 (mod 2 pi)
+    double sa, cr;  // |sin r| and cos r of the current NCO phase, double
+    double r;       // that phase reduced
     int kq;
-    bool generic_next;  // c0/s0/r/kq are not valid: use the general atan2 at the next step
+    bool generic_next;  // sa/cr/r/kq are not valid (fbI/fbQ are): use the general atan2 at the next step
     double magic;       // 1.5 * 2^(E+29), E = binade of the current NCO phase: td + magic - magic rounds td to float precision
 };
-// 1.5 * 2^(E+29) for the binade E of v: adding it to a number of that binade leaves exactly 24 significant bits (RNE).
-SDRB_HD double float_round_magic(double v) {
-    const uint64_t b = dbits(v);
-    const uint64_t m = ((b & 0x7FF0000000000000ull) + (29ull << 52)) | (1ull << 51);
+SDRB_HD uint32_t dhi(double v) {
 #if defined(__CUDA_ARCH__)
-    return __longlong_as_double((long long)m);
+    return (uint32_t)__double2hiint(v);
 #else
+    return (uint32_t)(dbits(v) >> 32);
+#endif
+}
+SDRB_HD uint32_t dlo(double v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(v);
+#else
+    return (uint32_t)dbits(v);
+#endif
+}
+SDRB_HD double mkd(uint32_t hi, uint32_t lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    uint64_t b = ((uint64_t)hi << 32) | lo;
     double o;
-    memcpy(&o, &m, 8);
+    memcpy(&o, &b, 8);
     return o;
 #endif
 }
+SDRB_HD uint32_t fbits(float v) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(v);
+#else
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    return b;
+#endif
+}
+SDRB_HD float bitsf(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    float v;
+    memcpy(&v, &b, 4);
+    return v;
+#endif
+}
+// 1.5 * 2^(E+29) for the binade E of v: adding it to a number of that binade leaves exactly 24 significant bits (RNE).
+SDRB_HD double float_round_magic(double v) { return mkd(((dhi(v) & 0x7FF00000u) + (29u << 20)) | (1u << 19), 0u); }
 constexpr double kMagicRint = 6755399441055744.0;  // 1.5 * 2^52: x + magic - magic = rint(x), integer in the low word
 constexpr int kAtanTolLog2 = -43;                  // absolute error bound of the rotated phase detector, see above
+
+// Conversions without the conversion unit.  The recurrence below crosses float <-> double four times per sample and an
+// F2F costs ~19 cycles each way (and 8 cycles of a pipe that two conversions in a row have to share); for operands
+// whose sign and range are known the same result takes two integer operations.
+//   d2f_known: RN_float(v) for a double that is NOT within the rejection distance of a float rounding tie (the callers
+//   test that separately), float-normal, and whose top nibble N (sign, three high exponent bits) is known:
+//   K = (((N & 1) ^ (N >> 3)) << 31) + 0x40000000.  (v >> 28 keeps one guard bit; +1, >>1 rounds half up.)
+SDRB_HD uint32_t d2f_known(double v, uint32_t K) {
+    const uint32_t v28 = (dhi(v) << 4) | (dlo(v) >> 28);
+    return K + ((v28 + 1u) >> 1);
+}
+SDRB_HD uint32_t d2f_K(uint32_t hi) {
+    uint32_t K = (((hi << 3) ^ hi) & 0x80000000u) | 0x40000000u;
+#if defined(__CUDA_ARCH__)
+    asm("" : "+r"(K));  // one register, made beside the chain (the compiler would otherwise add the constant last, on it)
+#endif
+    return K;
+}
+//   f2d_pos: (double)p for a positive normal float.
+SDRB_HD double f2d_pos(float p) {
+    const uint32_t b = fbits(p);
+    return mkd(0x38000000u + (b >> 3), b << 29);
+}
 
 // v is within 2^kAtanTolLog2 of a float rounding boundary (or too small for the bound to mean anything)
 SDRB_HD bool near_float_boundary_abs(double v) {
@@ -460,28 +518,33 @@ SDRB_HD bool near_float_boundary_abs(double v) {
     return dist <= (1u << (52 + kAtanTolLog2 - e));
 }
 
-// quarter-turn reduction + polynomials; false if the result must not be trusted (tiny r, huge x)
-SDRB_HD bool sincos_reduced(double x, double& s, double& c, double& r_out, int& q_out) {
-    double tm = dfma(x, kTwoOverPi, kMagicRint);
-    double kd = dadd(tm, -kMagicRint);
-    int q = (int)(uint32_t)dbits(tm) & 3;
-    double r = dfma(-kd, kP2, dfma(-kd, kP1, x));       // exact: x is a float, k*P1 and k*P2 are exact
-    double tail = dfma(kd, kP3, dmul(kd, kP4Rest));
-    r = dadd(r, -tail);
-    double sr, cr_;
-    sincos_poly(r, sr, cr_);
-    sincos_quadrant(q, sr, cr_, s, c);
+// Quarter-turn reduction with two fused steps: r = (x - k*PIO2H) - k*PIO2M.  Each fma rounds once, relative to a
+// result of the size of r, and PIO2H + PIO2M is pi/2 to 2^-107, so r is good to ~2^-52 relative for every k < 2^31
+// as long as |r| >= 2^-30 (which holds for every float argument below kReduceLimit, see sincos_fast).
+// Returns |sin r| and cos r; false if the result must not be trusted (tiny r).
+SDRB_HD bool sincos_reduce2(double x, double& sa, double& cr_, double& r_out, int& q_out) {
+    const double tm = dfma(x, kTwoOverPi, kMagicRint);
+    const double kd = dadd(tm, -kMagicRint);
+    const int q = (int)dlo(tm) & 3;
+    const double r = dfma(-kd, kPio2M, dfma(-kd, kPio2H, x));
+    const double ra = fabs(r);
+    sincos_poly2(r, ra, sa, cr_);
     r_out = r;
     q_out = q;
-    return !((kd != 0.0) && fabs(r) < 0x1p-30);
+    return !(ra < 0x1p-30);
+}
+// (sin theta, cos theta) from the reduced pieces
+SDRB_HD void pll_cs(double sa, double cr_, double r, int kq, double& s0, double& c0) {
+    sincos_quadrant(kq, r < 0.0 ? -sa : sa, cr_, s0, c0);
 }
 
 // cos_f with the leaner reduction: no rint, one acceptance test; anything doubtful goes to cos_f itself
 SDRB_HD float cos_lean_f(float t) {
     const double x = (double)t;
-    double ds, dc, r;
+    double sa, cr_, r, ds, dc;
     int q;
-    const bool ok = sincos_reduced(x, ds, dc, r, q);
+    const bool ok = sincos_reduce2(x, sa, cr_, r, q);
+    pll_cs(sa, cr_, r, q, ds, dc);
     if (!(fabs(x) < kReduceLimit) || !ok || near_float_boundary(dc)) return cos_f(t);
     return (float)dc;
 }
@@ -489,14 +552,16 @@ SDRB_HD float cos_lean_f(float t) {
 SDRB_HD void pll_fast_sincos(float trigArg, PllFast& f) {
     double x = (double)trigArg;
     f.magic = float_round_magic(x);
-    bool ok = fabs(x) < kReduceLimit && trigArg != 0.0f;
+    bool ok = fabs(x) < kReduceLimit && fabs(x) > 0x1p-100;
     if (ok) {
-        double ds, dc, r;
+        double sa, cr_, r;
         int q;
-        ok = sincos_reduced(x, ds, dc, r, q) && !near_float_boundary(ds) && !near_float_boundary(dc);
+        ok = sincos_reduce2(x, sa, cr_, r, q) && !near_float_boundary(sa) && !near_float_boundary(cr_);
         if (ok) {
-            f.s0 = ds;
-            f.c0 = dc;
+            double ds, dc;
+            pll_cs(sa, cr_, r, q, ds, dc);
+            f.sa = sa;
+            f.cr = cr_;
             f.r = r;
             f.kq = q;
             f.fbQ = (float)ds;
@@ -509,11 +574,23 @@ SDRB_HD void pll_fast_sincos(float trigArg, PllFast& f) {
         f.generic_next = true;
     }
 }
+// fbI/fbQ from the reduced pieces (the speculative steps do not keep them up to date)
+SDRB_HD void pll_fast_sync_fb(PllFast& f) {
+    if (f.generic_next) return;
+    double ds, dc;
+    pll_cs(f.sa, f.cr, f.r, f.kq, ds, dc);
+    f.fbQ = (float)ds;
+    f.fbI = (float)dc;
+}
 
 SDRB_HD void pll_fast_load(PllFast& f, const PllState& st, const PllCoef& k) {
     f.integ = st.integrator;
     f.phase = st.phaseEst;
     f.trigOffset = st.trigOffset;
+    f.sa = 0.0;
+    f.cr = 1.0;
+    f.r = 0.0;
+    f.kq = 0;
     // the phase the carried feedbackI/Q were computed from (/root/reference/src/pll.cpp:47 with the carried values)
     float trigArg = (float)dadd(dmul(k.w, st.trigOffset), (double)st.phaseEst);
     pll_fast_sincos(trigArg, f);
@@ -522,7 +599,8 @@ SDRB_HD void pll_fast_load(PllFast& f, const PllState& st, const PllCoef& k) {
     f.fbI = st.feedbackI;
     f.fbQ = st.feedbackQ;
 }
-SDRB_HD void pll_fast_store(const PllFast& f, PllState& st) {
+SDRB_HD void pll_fast_store(PllFast& f, PllState& st) {
+    pll_fast_sync_fb(f);
     st.feedbackI = f.fbI;
     st.feedbackQ = f.fbQ;
     st.integrator = f.integ;
@@ -530,15 +608,26 @@ SDRB_HD void pll_fast_store(const PllFast& f, PllState& st) {
     st.trigOffset = f.trigOffset;
 }
 
-// One sample.  rin = 1.0 / (double)in, computed off the critical path by the caller.  Returns trigArg.
+// 1/|in| for the rotated phase detector, or +inf when `in` is outside the range the speculative step handles
+// (zero, subnormal, tiny, huge, inf, NaN): an infinite reciprocal makes the step's result NaN, which its range test
+// rejects, and the careful path takes over.  `approx` is any approximation of 1/|in| good to 2^-22 relative.
+SDRB_HD double pll_guard_recip(float in, double approx) {
+    const uint32_t ex = (fbits(in) >> 23) & 0xFFu;  // accepted: 2^-90 <= |in| < 2^90
+    return (ex - (127u - 90u)) < 180u ? approx : (double)INFINITY;
+}
+
+// One sample, careful form.  rin = 1/|in| from pll_guard_recip (only its finite values are used).  Returns trigArg.
 SDRB_HD float pll_step_fast(float in, double rin, PllFast& f, const PllCoef& k, const AtanTab& tab) {
+    pll_fast_sync_fb(f);  // the speculative steps leave fbI/fbQ behind
     const float x = fmul(in, f.fbI);
     const float y = fmul(in, -f.fbQ);
     float errorD;
-    bool ok = !f.generic_next && x != 0.0f && y != 0.0f;
+    bool ok = !f.generic_next && x != 0.0f && y != 0.0f && rin < 1e300;
     if (ok) {
-        double u = dfma((double)y, f.c0, dmul((double)x, f.s0));
-        double w = dmul(u, rin);
+        double s0, c0;
+        pll_cs(f.sa, f.cr, f.r, f.kq, s0, c0);
+        double u = dfma((double)y, c0, dmul((double)x, s0));
+        double w = dmul(u, in < 0.0f ? -rin : rin);
         int m = (f.kq + (in < 0.0f ? 2 : 0)) & 3;
         // -theta (+pi) = -r - m*pi/2, brought into (-pi, pi]:  m: 0 -> 0, 1 -> -pi/2, 3 -> +pi/2, 2 -> -+pi
         double mm = (m == 0) ? 0.0 : (m == 1) ? -1.0 : (m == 3) ? 1.0 : (f.r > 0.0 ? 2.0 : -2.0);
@@ -555,20 +644,24 @@ SDRB_HD float pll_step_fast(float in, double rin, PllFast& f, const PllCoef& k, 
     return trigArg;
 }
 
-// ---- speculative form: the same step without a single branch ----
-// Every acceptance test of pll_step_fast is a side computation OR-ed (bitwise, no short circuit) into `bad`;
-// nothing on the recurrence waits for it.  The caller runs a few steps, looks at `bad` once, and in the (rare,
-// ~1e-5 per step) case that any test failed restores the state it saved and repeats those steps with pll_step_fast.
-SDRB_HD unsigned ambig_rel(double v) {  // near_float_boundary, branch-free (also flags zero / float-subnormal)
-    const uint64_t b = dbits(v);
-    const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
-    // |low29 - 0x10000000| <= T  <=>  (low29 - (0x10000000 - T)) <= 2T as unsigned (one subtract, one compare)
-    const uint32_t off = (lo & 0x1FFFFFFFu) - (0x10000000u - kAmbigUlps);
-    return (unsigned)(off <= 2u * kAmbigUlps) | (unsigned)((hi & 0x7FF00000u) < ((1023u - 126u + 1u) << 20));
+// ---- speculative form: the same step without a single branch and without a conversion instruction on the chain ----
+// Every acceptance test is a side computation OR-ed (bitwise, no short circuit) into `bad`; nothing on the recurrence
+// waits for it.  The caller runs a few steps, looks at `bad` once, and in the (rare, ~1e-5 per step) case that any test
+// failed restores the state it saved and repeats those steps with pll_step_fast.
+//
+// The chain per sample: sa,cr -> float (2 integer ops) -> |in|*fa, |in|*fc (FMUL) -> double (1 integer op) -> two
+// DFMA -> errorD (2 integer ops) -> FMUL, FADD, FADD -> double (F2F) -> DADD, 2 DADD (float rounding) -> 2 (k) ->
+// 2 DFMA (r) -> 5 deep Estrin -> sa,cr.  Signs never travel on it:
+//   u/in = errorI*sin + errorQ*cos  over  in  =  (-1)^[r<0] * ( RN(|in| fc) * sa/|in|  -  RN(|in| fa) * cr/|in| )
+// for every quadrant (fa, fc = RN_float(sa), RN_float(cr); the quadrant's swap of sine and cosine and their signs
+// cancel between the products and the multipliers), so the float products are formed from magnitudes and the one
+// remaining sign is folded into the reciprocal beforehand.
+SDRB_HD unsigned ambig_rel_lo(double v) {  // within kAmbigUlps double-ulps of a float rounding tie (v float-normal)
+    const uint32_t off = (dlo(v) & 0x1FFFFFFFu) - (0x10000000u - kAmbigUlps);
+    return (unsigned)(off <= 2u * kAmbigUlps);
 }
 SDRB_HD unsigned ambig_abs(double v) {  // near_float_boundary_abs, branch-free
-    const uint64_t b = dbits(v);
-    const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+    const uint32_t lo = dlo(v), hi = dhi(v);
     const uint32_t E = (hi >> 20) & 0x7FFu;                      // biased exponent; accepted range e in [-17, 1]
     const uint32_t thr = 1u << ((1023u + 52u + (uint32_t)kAtanTolLog2 - E) & 31u);  // tolerance in units of 2^(e-52)
     const uint32_t off = (lo & 0x1FFFFFFFu) - 0x10000000u + thr;
@@ -576,58 +669,63 @@ SDRB_HD unsigned ambig_abs(double v) {  // near_float_boundary_abs, branch-free
 }
 
 SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, unsigned& bad) {
-    const float x = fmul(in, f.fbI);
-    const float y = fmul(in, -f.fbQ);
-    const int m = (f.kq + (in < 0.0f ? 2 : 0)) & 3;
-    // -theta (+pi) = -r - m*pi/2 in (-pi, pi]:  m: 0 -> 0, 1 -> -pi/2, 3 -> +pi/2, 2 -> -+pi (selects, no branches)
-    const double m2 = f.r > 0.0 ? 2.0 : -2.0;
-    const double m13 = (m & 2) ? 1.0 : -1.0;
-    const double mm = (m & 1) ? m13 : ((m & 2) ? m2 : 0.0);
-    const double base = dadd(dmul(mm, K(kKPio2H)), -f.r);
-    const double u = dfma((double)y, f.c0, dmul((double)x, f.s0));
-    const double w = dmul(u, rin);
-    const double e = dadd(base, dfma(mm, K(kKPio2M), w));
-    // Zero products need no test of their own: in = 0 (or subnormal, flushed by the caller's reciprocal) makes rin
-    // infinite and w NaN/inf, which fails |w| < 2^-22; y = 0 alone puts e at ~0 or ~+-pi, both rejected below; x = 0
-    // alone (an underflowed in*cos) is an ordinary small perturbation; both zero with a normal `in` cannot happen
-    // because max(|cos|, |sin|) >= 0.7.
-    bad |= (unsigned)!(fabs(w) < 0x1p-22) | (unsigned)!(fabs(e) < 3.14159) | ambig_abs(e);
-    const float errorD = (float)e;
+    // -- beside the chain: needs only `in` and the previous step's reduction --
+    const uint32_t rhi = dhi(f.r);
+    const uint32_t rs = rhi & 0x80000000u;  // r < 0
+    const unsigned m = ((unsigned)f.kq + ((fbits(in) >> 31) << 1)) & 3u;
+    // -theta (+pi) = -r - m*pi/2 in (-pi, pi]:  mm = 0, -1, -+2 (by the sign of r), +1 for m = 0, 1, 2, 3
+    const uint32_t mmhi = (m & 1u) ? ((m & 2u) ? 0x3FF00000u : 0xBFF00000u) : ((m & 2u) ? (0xC0000000u ^ rs) : 0u);
+    const double mm = mkd(mmhi, 0u);
+    const double base = dfma(mm, K(kKPio2M), dfma(mm, K(kKPio2H), -f.r));
+    const uint32_t bh = dhi(base);
+    const uint32_t Ke = d2f_K(bh);
+    const double ars = mkd(dhi(rin) ^ rs, dlo(rin));  // (-1)^[r<0] / |in|
+    const double ma = dmul(f.sa, ars), mc = dmul(f.cr, -ars);
+    // -- the chain --
+    const float fa = bitsf(d2f_known(f.sa, 0xC0000000u)), fc = bitsf(d2f_known(f.cr, 0xC0000000u));
+    const float pa = fmul(fabsf(in), fa), pc = fmul(fabsf(in), fc);
+    const double e = dfma(f2d_pos(pc), ma, dfma(f2d_pos(pa), mc, base));
+    const float errorD = bitsf(d2f_known(e, Ke));
     f.integ = fadd(f.integ, fmul(k.Ki, errorD));
     f.phase = fadd(fadd(f.phase, fmul(k.Kp, errorD)), f.integ);
     f.trigOffset = dadd(f.trigOffset, 1.0);
-    const double td = dadd(dmul(k.w, f.trigOffset), (double)f.phase);
-    const float trigArg = (float)td;
-    // (double)trigArg without the float round trip: td + M - M with M = 1.5 * 2^(E+29) rounds td to 24 significant bits,
+#if defined(SDRB_PLL_PHASE_INTCONV)
+    const uint32_t pb = fbits(f.phase);  // (double)phase by hand: sign | (exponent + 896, mantissa << 29); zero/subnormal/inf/NaN -> bad
+    const double phd = mkd((((pb & 0x7FFFFFFFu) >> 3) + 0x38000000u) | (pb & 0x80000000u), pb << 29);
+    bad |= (unsigned)((((pb >> 23) & 0xFFu) - 1u) >= 254u);
+#else
+    const double phd = (double)f.phase;
+#endif
+    const double td = dadd(dmul(k.w, f.trigOffset), phd);
+    // (double)(float)td without the round trip: td + M - M with M = 1.5 * 2^(E+29) rounds td to 24 significant bits,
     // to nearest even, exactly like the conversion, provided td lies in the binade E that M was built for.  M comes from
-    // the previous step's phase (the binade changes once per doubling of the phase); a mismatch counts as bad.
+    // the previous step's phase (the binade changes once per doubling of the phase); a mismatch counts as bad, and so
+    // the range tests of the phase (below kReduceLimit, not tiny) only have to be made where M is made.
     const double xd = dadd(dadd(td, f.magic), -f.magic);
-    const double magic_next = float_round_magic(td);
-    bad |= (unsigned)!(fabs(td) < kReduceLimit) | (unsigned)!(fabs(td) > 0x1p-100) | (unsigned)(magic_next != f.magic);
-    f.magic = magic_next;
-    // quarter-turn reduction and polynomials (sincos_reduced, inlined so that its test joins `bad`).  The quadrant
+    // quarter-turn reduction and polynomials (sincos_reduce2, inlined so that its test joins `bad`).  The quadrant
     // count must come from xd, not td: once the phase passes 2^22 the float grid is coarser than pi/4, td and xd can
     // be a radian apart, and a count taken from td would leave |r| far outside the range of the kernels below.
     const double tm = dfma(xd, K(kK2OverPi), kMagicRint);
     const double kd = dadd(tm, -kMagicRint);
-#if defined(__CUDA_ARCH__)
-    const int q = __double2loint(tm) & 3;  // 32-bit all the way (the 64-bit route costs extra compare halves)
-#else
-    const int q = (int)(uint32_t)dbits(tm) & 3;
-#endif
-    double r = dfma(-kd, kP2, dfma(-kd, kP1, xd));
-    r = dadd(r, -dfma(kd, K(kKP3), dmul(kd, K(kKP4Rest))));
-    double sr, cr_, ds, dc;
-    sincos_poly(r, sr, cr_);
-    sincos_quadrant(q, sr, cr_, ds, dc);
-    bad |= ((unsigned)(kd != 0.0) & (unsigned)(fabs(r) < 0x1p-30)) | ambig_rel(ds) | ambig_rel(dc);
-    f.s0 = ds;
-    f.c0 = dc;
+    const int q = (int)dlo(tm) & 3;
+    const double r = dfma(-kd, K(kKPio2M), dfma(-kd, K(kKPio2H), xd));
+    const uint32_t rah = dhi(r) & 0x7FFFFFFFu;
+    double sa, cr_;
+    sincos_poly2(r, mkd(rah, dlo(r)), sa, cr_);  // |r| joins only at the last fma of the sine
+    // -- the tests --
+    // e: NaN/inf (an out-of-range `in`), the wrap (|e| < pi), the linearisation (|e - base| = |u/in| < 2^-22), the
+    // float rounding of e, and base so close to +-2 that e and base could differ in the nibble d2f_known was told
+    const double wq = dadd(e, -base);
+    bad |= (unsigned)((dhi(e) & 0x7FFFFFFFu) >= 0x400921F9u) | (unsigned)((dhi(wq) & 0x7FFFFFFFu) >= 0x3E900000u) | ambig_abs(e) |
+           (unsigned)(((bh & 0x7FFFFFFFu) - 0x3FFFFFFFu) <= 1u);
+    // td left the binade of M; r tiny; sa / cr near a float rounding tie
+    bad |= (unsigned)((((dhi(td) & 0x7FF00000u) + (29u << 20)) | (1u << 19)) != dhi(f.magic)) | (unsigned)(rah < 0x3E100000u) |
+           ambig_rel_lo(sa) | ambig_rel_lo(cr_);
+    f.sa = sa;
+    f.cr = cr_;
     f.r = r;
     f.kq = q;
-    f.fbQ = (float)ds;
-    f.fbI = (float)dc;
-    return trigArg;
+    return (float)td;
 }
 
 #if defined(__CUDA_ARCH__)
@@ -645,6 +743,7 @@ SDRB_RARE void pll_redo4(float i0, float i1, float i2, float i3, double r0, doub
 }
 
 // Four consecutive samples: speculative run, verified once; the careful path only on failure.
+// r0..r3 = pll_guard_recip of the samples.
 SDRB_HD void pll_chunk4(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, PllFast& f,
                         const PllCoef& k, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3) {
     const PllFast saved = f;

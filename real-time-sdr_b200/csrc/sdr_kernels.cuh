@@ -460,15 +460,18 @@ struct PllArgs {
     int n_streams;
 };
 
-constexpr int kPllThreads = 128;  // four warps = one per SM sub-partition: each has a scheduler (and FP64 lanes) to itself
+#ifndef SDRB_PLL_THREADS
+#define SDRB_PLL_THREADS 128
+#endif
+constexpr int kPllThreads = SDRB_PLL_THREADS;  // four warps = one per SM sub-partition: each has a scheduler (and FP64 lanes) to itself
 
 // 1/v for the rotated phase detector: w = u * (1/in) is a <= 2^-22 rad correction whose absolute error may be 2^-45,
 // so a relative 2^-23 is enough: the FP32 reciprocal approximation (MUFU.RCP, 1 ulp) widened to double.  v = 0 or
 // subnormal gives inf, which the step's |w| test turns into the general path.
 __device__ __forceinline__ double pll_recip(float v) {
     float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return (double)r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fabsf(v)));
+    return cr::pll_guard_recip(v, (double)r);
 }
 
 constexpr int kPllTileChunks = 8;  // 32 steps per staged tile

@@ -128,7 +128,7 @@ void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, flo
     int i = 0;
     for (; i + 4 <= n; i += 4) {  // the kernel's chunking: 4 speculative steps, verified once
         float c[4] = {in[i], in[i + 1], in[i + 2], in[i + 3]}, th[4];
-        auto recip = [](float v) { return (fabsf(v) < 1.17549435e-38f) ? (double)INFINITY : 1.0 / (double)v; };  // device: rcp.approx.ftz
+        auto recip = [](float v) { return pll_guard_recip(v, 1.0 / fabs((double)v)); };  // device: rcp.approx.ftz of |v|
         double r[4] = {recip(c[0]), recip(c[1]), recip(c[2]), recip(c[3])};
         PllFast probe = f;
         unsigned bad = f.generic_next ? 1u : 0u;
@@ -139,7 +139,7 @@ void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, flo
         for (int j = 0; j < 4; j++) out[i + j + 1] = nco_out(th[j], k);
     }
     for (; i < n; i++) {
-        float th = pll_step_fast(in[i], 1.0 / (double)in[i], f, k, kTab);
+        float th = pll_step_fast(in[i], pll_guard_recip(in[i], 1.0 / fabs((double)in[i])), f, k, kTab);
         out[i + 1] = nco_out(th, k);
     }
     pll_fast_store(f, st);
