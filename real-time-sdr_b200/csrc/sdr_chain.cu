@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/sdr_b200.h"
@@ -292,8 +293,15 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
             a.loop[1].st = c->d_pll[1];
             a.loop[1].coef = cr::pll_coef(114e3f, (float)c->cfg.if_Fs, 0.5f, 0.0f, 0.001f);  // src/rds.cpp:119
         }
-        dim3 grid((S + kPllThreads - 1) / kPllThreads, c->rds ? 2 : 1);
-        k_pll<<<grid, kPllThreads, kPllSmemBytes, sp>>>(a);
+        const int loops = c->rds ? 2 : 1;
+        auto launch = [&](auto threads_tag) {
+            constexpr int T = decltype(threads_tag)::value;
+            dim3 grid((S + T - 1) / T, loops);
+            k_pll<T><<<grid, T, kPllSmemBytes, sp>>>(a);
+        };
+        if ((S + 31) / 32 * loops <= kPllMaxCtas) launch(std::integral_constant<int, 32>{});
+        else if ((S + 63) / 64 * loops <= kPllMaxCtas) launch(std::integral_constant<int, 64>{});
+        else launch(std::integral_constant<int, 128>{});
         if ((rc = check_launch(c, "k_pll", sp))) return rc;
     }
     if (ov) {
@@ -605,8 +613,12 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
             TRY(dalloc(c, (void**)&c->d_rclean, sizeof(float) * I.rds_block * S));
         }
     }
-    static_assert(kPllTileBytes <= kPllSmemBytes, "PLL input ring must fit the reserved shared memory");
-    if (c->stereo) TRYCU(cudaFuncSetAttribute(k_pll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
+    static_assert(pll_tile_bytes(kPllThreads) <= kPllSmemBytes, "PLL input ring must fit the reserved shared memory");
+    if (c->stereo) {
+        TRYCU(cudaFuncSetAttribute(k_pll<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
+        TRYCU(cudaFuncSetAttribute(k_pll<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
+        TRYCU(cudaFuncSetAttribute(k_pll<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
+    }
     if (c->rds) {
         const int rrc_tiles = (I.rds_block + kRrcTile - 1) / kRrcTile;
         const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;

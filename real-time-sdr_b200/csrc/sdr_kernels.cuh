@@ -460,10 +460,11 @@ struct PllArgs {
     int n_streams;
 };
 
-#ifndef SDRB_PLL_THREADS
-#define SDRB_PLL_THREADS 128
-#endif
-constexpr int kPllThreads = SDRB_PLL_THREADS;  // four warps = one per SM sub-partition: each has a scheduler (and FP64 lanes) to itself
+// CTA size of k_pll: one warp per SM measures fastest (316 cycles per sample against 331 with four warps, one per
+// sub-partition: the warps of one SM still share its instruction and constant caches), so the launch uses the
+// smallest size that keeps the PLL on at most kPllMaxCtas SMs and leaves the rest to the FIR kernels.
+constexpr int kPllThreads = 128;  // largest CTA; also the block size of the generic single-call kernel
+constexpr int kPllMaxCtas = 64;
 
 // 1/v for the rotated phase detector: w = u * (1/in) is a <= 2^-22 rad correction whose absolute error may be 2^-45,
 // so a relative 2^-23 is enough: the FP32 reciprocal approximation (MUFU.RCP, 1 ulp) widened to double.  v = 0 or
@@ -477,16 +478,20 @@ __device__ __forceinline__ double pll_recip(float v) {
 constexpr int kPllTileChunks = 8;  // 32 steps per staged tile
 
 constexpr int kPllTileRow = 4 * kPllTileChunks + 4;
-constexpr size_t kPllTileBytes = sizeof(float) * 3 * kPllThreads * kPllTileRow;
+constexpr size_t pll_tile_bytes(int threads) { return sizeof(float) * 3 * threads * kPllTileRow; }
 // The launch asks for (nearly) all of an SM's shared memory, far more than the input ring needs: no other CTA then fits
-// on that SM, so in overlap mode the FIR kernels of the neighbouring blocks cannot steal issue slots from the four
-// latency-bound warps (1024 streams x 2 loops = 16 CTAs = 16 of 148 SMs).
-constexpr size_t kPllSmemBytes = 225 * 1024;
+// on that SM, so in overlap mode the FIR kernels of the neighbouring blocks cannot steal issue slots from the
+// latency-bound warps.
+#ifndef SDRB_PLL_SMEM_KB
+#define SDRB_PLL_SMEM_KB 225
+#endif
+constexpr size_t kPllSmemBytes = SDRB_PLL_SMEM_KB * 1024;
 
-__global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
     __shared__ cr::AtanTab tab;
     extern __shared__ __align__(16) float pll_dyn_smem[];
-    float (*tile)[kPllThreads][kPllTileRow] = reinterpret_cast<float (*)[kPllThreads][kPllTileRow]>(pll_dyn_smem);
+    float (*tile)[THREADS][kPllTileRow] = reinterpret_cast<float (*)[THREADS][kPllTileRow]>(pll_dyn_smem);
     {
         const cr::AtanTab init = SDRB_ATAN_TAB_INIT;
         if (threadIdx.x < 17) {
@@ -496,7 +501,7 @@ __global__ void __launch_bounds__(kPllThreads) k_pll(const PllArgs a) {
     }
     __syncthreads();
     const PllLoop& lp = a.loop[blockIdx.y];
-    const int s = blockIdx.x * kPllThreads + threadIdx.x;
+    const int s = blockIdx.x * THREADS + threadIdx.x;
     if (s >= a.n_streams) return;
     PllStateDev sd = lp.st[s];
     cr::PllState st{sd.feedbackI, sd.feedbackQ, sd.integrator, sd.phaseEst, sd.trigOffset};
