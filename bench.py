@@ -135,35 +135,87 @@ def cpu_reference_run(nblocks=98, steps=1, warmup=0):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled every few milliseconds by a thread while the timed region runs
+    (NVML in-process; `nvidia-smi -lms` as the fallback: it needs ~100 ms to start, so it is started before warm-up)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.rows = []
+    def __init__(self, index, pci_bus_id=None, period_s=0.004):
+        self.rows = []  # (t, sm_mhz, [reasons])
+        self.max_mhz = None
+        self.source = None
+        self._stop = threading.Event()
         self.proc = None
+        self.th = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if pci_bus_id:
+                try:
+                    h = nv.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode() if isinstance(pci_bus_id, str) else pci_bus_id)
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                    (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        mask = int(get_reasons(h))
+                        self.rows.append((time.perf_counter(), mhz, [n for b, n in bits if mask & b]))
+                    except Exception:
+                        pass
+                    self._stop.wait(period_s)
+
+            self.source = "nvml"
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            pass
         exe = shutil.which("nvidia-smi")
         if exe:
-            self.proc = subprocess.Popen([exe, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.source = "nvidia-smi"
+            self.proc = subprocess.Popen([exe, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+            c = [x.strip() for x in line.split(",")]
+            try:
+                mhz = float(c[0])
+                self.max_mhz = max(self.max_mhz or 0.0, float(c[1]))
+            except (ValueError, IndexError):
+                continue
+            self.rows.append((time.perf_counter(), mhz, [self.NAMES[i] for i in range(4) if len(c) >= 7 and c[3 + i].lower().startswith("active")]))
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
-        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(rows)}
+        """Summary of the samples taken inside [t0, t1] (perf_counter times of the timed region)."""
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi and NVML unavailable"], "samples": 0}
+        self._stop.set()
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+        elif self.th:
+            self.th.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        inside = len(rows)
+        if not rows:  # a region shorter than one sampling period: the nearest samples either side
+            rows = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:2]
+        sm = [r[1] for r in rows]
+        reasons = sorted({n for r in rows for n in r[2]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": inside, "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -189,7 +241,7 @@ def build_inputs(torch, gen, n_streams, bb, pitch, dev, first_station=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=1024, help="stations per GPU")
@@ -265,12 +317,19 @@ def main():
             ch.process_device(inputs[(first + i) % N_INPUTS].data_ptr(), pitch)
 
     # ---- device-resident throughput
+    sampler = None
+    if rank == 0:  # started before the warm-up so that it is already sampling when the timed region begins
+        pr = torch.cuda.get_device_properties(local_rank)
+        try:
+            bus_id = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        except Exception:
+            bus_id = None
+        sampler = ClockSampler(local_rank, bus_id)
     run_steps(args.warmup, 0)
     ch.join()
     barrier()
     launches0 = ch.launch_count()
     ch.set_profiling(True)  # one CUDA event pair per kernel launch, on the stream it runs on: averaged over the timed region
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)

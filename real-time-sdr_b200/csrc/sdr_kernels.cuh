@@ -230,6 +230,20 @@ __device__ __forceinline__ float unpack_u8(uint32_t u) {
     return __fmaf_rn(__uint_as_float(0x4B000000u | u), 0.0078125f, -65537.0f);
 }
 
+// IQ pair `WHICH` (0 or 1) of a 32-bit word of raw bytes I0 Q0 I1 Q1 -> (float I, float Q): two byte permutes build
+// 2^23 + u for both bytes, one packed FMA scales and recentres both (exact, as in unpack_u8).
+template <int WHICH>
+__device__ __forceinline__ float2 unpack_iq(uint32_t word) {
+    const uint32_t i = __byte_perm(word, 0x4B000000u, WHICH ? 0x7652u : 0x7650u);
+    const uint32_t q = __byte_perm(word, 0x4B000000u, WHICH ? 0x7653u : 0x7651u);
+    unsigned long long v, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(i), "r"(q));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(v), "l"(0x3C0000003C000000ull), "l"(0xC7800080C7800080ull));
+    float2 o;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+    return o;
+}
+
 // (float)(num / (double)I^2 + (double)Q^2), /root/reference/src/demod.cpp:9-18
 __device__ __forceinline__ float fm_discriminate(float I, float Q, float pI, float pQ) {
     if (I == 0.0f && Q == 0.0f) return 0.0f;
@@ -307,11 +321,40 @@ __global__ void __launch_bounds__(kRfThreads) k_rf_frontend(const __grid_constan
         __syncthreads();
     }
     // unpack to float2 (I, Q) in the padded, bank-conflict-free layout the FIR core reads
-    for (int u = threadIdx.x; u < NS; u += kRfThreads) {
-        const int g = g0 + u;
-        uint32_t pr = 0x8080u;  // beyond the block: the byte that unpacks to 0.0f
-        if (g < a.block_pairs) pr = *reinterpret_cast<const uint16_t*>(raw + (2 * g - A));
-        sx[pad_pos<L>(u)] = make_float2(unpack_u8(pr & 0xFFu), unpack_u8(pr >> 8));
+    if (((byte_lo - A) & 3) == 0) {
+        // Word path (always taken for even DECIM): one 32-bit word = two IQ pairs -> four PRMT, two packed FMAs, two
+        // 64-bit stores (6.5 instructions per pair; the pair-at-a-time loop below is 17).  Bytes past the end of the
+        // block (last tile only) are first overwritten with 128, the byte that unpacks to 0.0f.
+        if (a.tma_ok && g0 + NS > a.block_pairs) {
+            for (int o = 2 * a.block_pairs - A + 2 * (int)threadIdx.x; o < kRawBytes; o += 2 * kRfThreads)
+                *reinterpret_cast<uint16_t*>(raw + o) = 0x8080u;
+            __syncthreads();
+        }
+        // A sweep covers a whole number of padding blocks (L pairs = L/2 words each), so from one sweep to the next
+        // both addresses advance by compile-time constants: no index arithmetic in the (unrolled) loop.
+        constexpr int NW = (NS + 1) / 2;               // words in the tile
+        constexpr int HW = L / 2;                       // words per padding block (L is even)
+        constexpr int SW = (kRfThreads / HW) * HW;      // words per sweep (threads >= SW sit this phase out)
+        constexpr int SP = 2 * SW + 2 * SW / L;         // float2 slots per sweep
+        if (threadIdx.x < SW) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw) + ((byte_lo - A) >> 2) + threadIdx.x;
+            float2* d = &sx[pad_pos<L>(2 * threadIdx.x)];
+#pragma unroll
+            for (int i = 0; i < (NW + SW - 1) / SW; i++) {
+                if ((i + 1) * SW <= NW || (int)threadIdx.x + i * SW < NW) {
+                    const uint32_t word = rw[i * SW];
+                    d[i * SP] = unpack_iq<0>(word);
+                    d[i * SP + 1] = unpack_iq<1>(word);  // (for odd NS the last one lands in the spare slot past the tile)
+                }
+            }
+        }
+    } else {
+        for (int u = threadIdx.x; u < NS; u += kRfThreads) {
+            const int g = g0 + u;
+            uint32_t pr = 0x8080u;  // beyond the block: the byte that unpacks to 0.0f
+            if (g < a.block_pairs) pr = *reinterpret_cast<const uint16_t*>(raw + (2 * g - A));
+            sx[pad_pos<L>(u)] = make_float2(unpack_u8(pr & 0xFFu), unpack_u8(pr >> 8));
+        }
     }
     // carry the last pairs of this block to the next block's halo (one tile per stream does it)
     if (tile == 0)
@@ -326,11 +369,18 @@ __global__ void __launch_bounds__(kRfThreads) k_rf_frontend(const __grid_constan
 #pragma unroll
     for (int j = 0; j < kRfR; j++) sy[kRfR * threadIdx.x + j] = acc[j];
     __syncthreads();
-    for (int q = threadIdx.x + 1; q < kRfTile; q += kRfThreads) {
-        int m = m0 + q;
-        if (m < a.if_block) {
-            float2 c = sy[q], p = sy[q - 1];
-            ring_store(a.fm, s, m, fm_discriminate(c.x, c.y, p.x, p.y));
+    float* const fm_row = a.fm.cur + (size_t)s * a.fm.pitch;
+    float* const fm_halo = a.fm.nxt + (size_t)s * a.fm.pitch - a.fm.n;  // fm_halo[m] = slot of sample m in the next block's halo
+    const int halo_from = a.fm.n - a.fm.halo;
+#pragma unroll
+    for (int i = 0; i < kRfR; i++) {
+        const int q = threadIdx.x + 1 + i * kRfThreads;
+        const int m = m0 + q;
+        if (q < kRfTile && m < a.if_block) {
+            const float2 c = sy[q], p = sy[q - 1];
+            const float v = fm_discriminate(c.x, c.y, p.x, p.y);
+            fm_row[m] = v;
+            if (m >= halo_from) fm_halo[m] = v;
             if (a.i_ds) {
                 a.i_ds[(size_t)s * a.if_block + m] = c.x;
                 a.q_ds[(size_t)s * a.if_block + m] = c.y;
