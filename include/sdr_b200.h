@@ -84,6 +84,38 @@ int sdrb_pll(const float* d_in, size_t in_pitch, int n, float freq, float Fs, fl
 /* cdr(sps, signal) — include/rds_utilities.h:6, src/rds_utilities.cpp:4-21.  d_offset [n_streams]. */
 int sdrb_cdr(const float* d_x, size_t x_pitch, int n, int sps, int* d_offset, int n_streams, void* stream);
 
+/* manchester_decode(bits, symbols, block_count, half_symbol, start) — include/rds_utilities.h:8-9,
+ * src/rds_utilities.cpp:34-68.  d_symbols [n_streams][sym_pitch] (0/1), d_nsym [n_streams] symbols used per stream;
+ * d_state [n_streams] carries half_symbol/start in and out; d_bits [n_streams][bits_pitch] receives d_nbits[s]
+ * bits (at most 1 + nsym/2).  block_count == 0 re-estimates the pairing phase first (:42-51), as the reference does. */
+typedef struct {
+    int32_t half_symbol, start;
+} sdrb_manchester_state;
+int sdrb_manchester_decode(const int32_t* d_symbols, size_t sym_pitch, const int32_t* d_nsym, int block_count,
+                           sdrb_manchester_state* d_state, int32_t* d_bits, size_t bits_pitch, int32_t* d_nbits, int n_streams,
+                           void* stream);
+
+/* differential_decode(decoded, bits, last_bit, block_num) — include/rds_utilities.h:11-12,
+ * src/rds_utilities.cpp:70-88.  d_last_bit [n_streams] in/out; d_decoded receives d_nbits[s] bits.  A stream with
+ * d_nbits[s] == 0 (undefined behaviour in the reference) is left untouched. */
+int sdrb_differential_decode(const int32_t* d_bits, size_t bits_pitch, const int32_t* d_nbits, int block_num, int32_t* d_last_bit,
+                             int32_t* d_decoded, size_t dec_pitch, int n_streams, void* stream);
+
+/* start_frame_sync(idx = 0, stream, carry, reg, ...) with check_block — include/rds_utilities.h:14-19,
+ * src/rds_utilities.cpp:352-400.  The d_nbits[s] (<= max_nbits <= 8128) new bits of each stream are appended to the
+ * carried tail in d_state; d_groups [n_streams][groups_pitch] receives the group register at every A,B,C,D completion
+ * (the value the reference hands to parse(), see sdrb_rds_parse below), d_ngroups [n_streams] their number (which may
+ * exceed max_groups: only the first max_groups are stored).  A zero-initialised state is the reference's initial state. */
+typedef struct {
+    uint64_t reg;      /* src/rds.cpp:67 */
+    int32_t window[4]; /* last matched offsets, 0 A, 1 B, 2 C, 3 C', 4 D (src/rds.cpp:70) */
+    int32_t nwindow;
+    int32_t ncarry;
+    uint8_t carry[64]; /* unread tail of the previous call (src/rds_utilities.cpp:398-399) */
+} sdrb_framesync_state;
+int sdrb_frame_sync(const int32_t* d_bits, size_t bits_pitch, const int32_t* d_nbits, int max_nbits, sdrb_framesync_state* d_state,
+                    uint64_t* d_groups, size_t groups_pitch, int32_t* d_ngroups, int max_groups, int n_streams, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3. The fused receive chain: RF_frontend + mono|stereo + rds for n_streams stations
  *    (include/rffrontend.h:5, mono.h:5, stereo.h:4, rds.h:4; struct args, include/args.h:6-19).

@@ -26,6 +26,7 @@ EXPORTS = [
     "sdrb_chain_state_bytes", "sdrb_chain_state_save", "sdrb_chain_state_load", "sdrb_chain_kernel_times",
     "sdrb_chain_set_profiling", "sdrb_chain_launch_count", "sdrb_chain_set_overlap", "sdrb_pinned_alloc",
     "sdrb_pinned_free", "sdrb_chain_set_stream", "sdrb_chain_join", "sdrb_chain_read_results",
+    "sdrb_manchester_decode", "sdrb_differential_decode", "sdrb_frame_sync",
 ]
 
 
@@ -45,6 +46,8 @@ class RdsRecord(C.Structure):
                 ("bits", C.c_uint8 * 48), ("groups", C.c_uint64 * 8)]
 
 
+MANCHESTER_STATE_DTYPE = np.dtype([("half_symbol", "<i4"), ("start", "<i4")])
+FRAMESYNC_STATE_DTYPE = np.dtype([("reg", "<u8"), ("window", "<i4", (4,)), ("nwindow", "<i4"), ("ncarry", "<i4"), ("carry", "u1", (64,))])
 RDS_RECORD_DTYPE = np.dtype([("cdr_offset", "<i4"), ("n_symbols", "<i4"), ("n_bits", "<i4"), ("n_groups", "<i4"),
                              ("bits", "u1", (48,)), ("groups", "<u8", (8,))])
 assert RDS_RECORD_DTYPE.itemsize == C.sizeof(RdsRecord)
@@ -87,6 +90,9 @@ def load(path: str | None = None) -> C.CDLL:
     L.sdrb_fm_demod.argtypes = [vp, vp, sz, ci, vp, vp, sz, ci, vp]
     L.sdrb_pll.argtypes = [vp, sz, ci, cf, cf, cf, cf, cf, vp, vp, sz, ci, vp]
     L.sdrb_cdr.argtypes = [vp, sz, ci, ci, vp, ci, vp]
+    L.sdrb_manchester_decode.argtypes = [vp, sz, vp, ci, vp, vp, sz, vp, ci, vp]
+    L.sdrb_differential_decode.argtypes = [vp, sz, vp, ci, vp, vp, sz, ci, vp]
+    L.sdrb_frame_sync.argtypes = [vp, sz, vp, ci, vp, vp, sz, vp, ci, ci, vp]
     L.sdrb_config_for_mode.argtypes = [ci, ci, ci, C.POINTER(Config)]
     L.sdrb_chain_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     L.sdrb_chain_destroy.argtypes = [vp]

@@ -1027,4 +1027,33 @@ int sdrb_cdr(const float* d_x, size_t x_pitch, int n, int sps, int* d_offset, in
     return SDRB_OK;
 }
 
+int sdrb_manchester_decode(const int32_t* d_symbols, size_t sym_pitch, const int32_t* d_nsym, int block_count,
+                           sdrb_manchester_state* d_state, int32_t* d_bits, size_t bits_pitch, int32_t* d_nbits, int n_streams, void* stream) {
+    if (!d_symbols || !d_nsym || !d_state || !d_bits || !d_nbits || n_streams < 1) return fail(SDRB_ERR_INVALID, "bad argument");
+    static_assert(sizeof(sdrb_manchester_state) == sizeof(ManchesterState), "ABI struct");
+    k_manchester_generic<<<n_streams, 32, 0, (cudaStream_t)stream>>>(d_symbols, sym_pitch, d_nsym, block_count,
+                                                                      reinterpret_cast<ManchesterState*>(d_state), d_bits, bits_pitch, d_nbits);
+    CU(cudaGetLastError());
+    return SDRB_OK;
+}
+
+int sdrb_differential_decode(const int32_t* d_bits, size_t bits_pitch, const int32_t* d_nbits, int block_num, int32_t* d_last_bit,
+                             int32_t* d_decoded, size_t dec_pitch, int n_streams, void* stream) {
+    if (!d_bits || !d_nbits || !d_last_bit || !d_decoded || n_streams < 1) return fail(SDRB_ERR_INVALID, "bad argument");
+    k_differential_generic<<<n_streams, 32, 0, (cudaStream_t)stream>>>(d_bits, bits_pitch, d_nbits, block_num, d_last_bit, d_decoded, dec_pitch);
+    CU(cudaGetLastError());
+    return SDRB_OK;
+}
+
+int sdrb_frame_sync(const int32_t* d_bits, size_t bits_pitch, const int32_t* d_nbits, int max_nbits, sdrb_framesync_state* d_state,
+                    uint64_t* d_groups, size_t groups_pitch, int32_t* d_ngroups, int max_groups, int n_streams, void* stream) {
+    if (!d_bits || !d_nbits || !d_state || !d_groups || !d_ngroups || max_groups < 0 || n_streams < 1) return fail(SDRB_ERR_INVALID, "bad argument");
+    if (max_nbits < 0 || max_nbits + 64 > kFrameSyncMaxBits) return fail(SDRB_ERR_INVALID, "sdrb_frame_sync: at most 8128 new bits per call");
+    static_assert(sizeof(sdrb_framesync_state) == sizeof(FrameSyncState), "ABI struct");
+    k_frame_sync_generic<<<n_streams, 32, 0, (cudaStream_t)stream>>>(d_bits, bits_pitch, d_nbits, reinterpret_cast<FrameSyncState*>(d_state),
+                                                                      reinterpret_cast<unsigned long long*>(d_groups), groups_pitch, d_ngroups, max_groups);
+    CU(cudaGetLastError());
+    return SDRB_OK;
+}
+
 }  // extern "C"

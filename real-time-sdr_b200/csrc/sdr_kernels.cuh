@@ -1213,4 +1213,139 @@ __global__ void __launch_bounds__(64) k_cdr_generic(const float* x, size_t x_pit
     if (threadIdx.x == 0) offset[s] = best;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stand-alone batched bit-level primitives (sdrb_manchester_decode, sdrb_differential_decode, sdrb_frame_sync):
+// one warp per stream.  The fused chain does the same work inside k_rds_backend.
+// ------------------------------------------------------------------------------------------------
+struct ManchesterState {  // mirrors sdrb_manchester_state
+    int32_t half_symbol, start;
+};
+
+// manchester_decode, /root/reference/src/rds_utilities.cpp:34-68.  bits[q] = carried half symbol (if the carried
+// `start` is set) followed by symbols[i] for i = start, start+2, ... < n-1, where `start` is first re-estimated from the
+// pair agreement scores when block_count == 0 (:42-51); then the carry for the next call (:61-66).
+__global__ void __launch_bounds__(32) k_manchester_generic(const int32_t* symbols, size_t sym_pitch, const int32_t* nsym, int block_count,
+                                                           ManchesterState* state, int32_t* bits, size_t bits_pitch, int32_t* nbits) {
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int32_t* sym = symbols + (size_t)s * sym_pitch;
+    int32_t* out = bits + (size_t)s * bits_pitch;
+    const int n = nsym[s];
+    const ManchesterState st = state[s];
+    const int lead = st.start ? 1 : 0;  // the carried half symbol is emitted first (:38-40), before any re-estimate
+    int start = st.start;
+    if (block_count == 0) {
+        int score = 0;
+        for (int i = 2 * lane; i < n - 1; i += 64) score += sym[i] ^ sym[i + 1];
+        for (int j = 2 * lane + 1; j < n - 1; j += 64) score -= sym[j] ^ sym[j + 1];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, o);
+        start = score < 0;
+    }
+    const int npairs = (n - 1 > start) ? (n - 1 - start + 1) / 2 : 0;
+    const int nb = lead + npairs;
+    for (int q = lane; q < nb; q += 32) out[q] = (lead && q == 0) ? st.half_symbol : sym[start + 2 * (q - lead)];
+    if (lane == 0) {
+        nbits[s] = nb;
+        ManchesterState o = st;
+        if (n > 0) {  // (n == 0: the reference reads symbols[-1]; the carried state is left as it is)
+            if ((n - start) & 1) { o.half_symbol = sym[n - 1]; o.start = 1; }
+            else o.start = 0;
+        }
+        state[s] = o;
+    }
+}
+
+// differential_decode, /root/reference/src/rds_utilities.cpp:70-88: decoded[0] = bits[0] (^ last_bit unless
+// block_num == 0), decoded[i] = bits[i] ^ bits[i-1] (the neighbour comes by warp shuffle, the chunk edge from the
+// previous chunk's last lane), last_bit = bits[n-1].  n == 0 (undefined in the reference) leaves last_bit alone.
+__global__ void __launch_bounds__(32) k_differential_generic(const int32_t* bits, size_t bits_pitch, const int32_t* nbits, int block_num,
+                                                             int32_t* last_bit, int32_t* decoded, size_t dec_pitch) {
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int32_t* b = bits + (size_t)s * bits_pitch;
+    int32_t* d = decoded + (size_t)s * dec_pitch;
+    const int n = nbits[s];
+    int edge = block_num == 0 ? 0 : last_bit[s];  // the bit before this chunk's lane 0
+    for (int q0 = 0; q0 < n; q0 += 32) {
+        const int q = q0 + lane;
+        const int v = q < n ? b[q] : 0;
+        int prev = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        if (lane == 0) prev = edge;
+        if (q < n) d[q] = v ^ prev;
+        edge = __shfl_sync(0xFFFFFFFFu, v, 31);
+    }
+    if (lane == 0 && n > 0) last_bit[s] = b[n - 1];
+}
+
+struct FrameSyncState {  // mirrors sdrb_framesync_state
+    uint64_t reg;
+    int32_t window[4];
+    int32_t nwindow;
+    int32_t ncarry;
+    uint8_t carry[64];
+};
+constexpr int kFrameSyncMaxBits = 8192;  // carried tail + new bits per call
+
+// start_frame_sync + check_block, /root/reference/src/rds_utilities.cpp:352-400: the new bits are appended to the
+// carried tail, every 26-bit window's syndrome is classified in parallel, then one lane walks the stream with the
+// reference's stepping rule (26 after a match, 1 otherwise, while idx < size-26), keeps the group register and the
+// window of the last four matched offsets, and reports `reg` at every A,B,C,D completion.
+__global__ void __launch_bounds__(32) k_frame_sync_generic(const int32_t* bits, size_t bits_pitch, const int32_t* nbits, FrameSyncState* state,
+                                                           unsigned long long* groups, size_t groups_pitch, int32_t* ngroups, int max_groups) {
+    __shared__ uint32_t sbuf[kFrameSyncMaxBits / 32 + 2];
+    __shared__ int8_t stype[kFrameSyncMaxBits];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int32_t* b = bits + (size_t)s * bits_pitch;
+    FrameSyncState* st = state + s;
+    const int ncarry = st->ncarry;
+    const int total = min(ncarry + max(nbits[s], 0), kFrameSyncMaxBits);
+    for (int w = lane; w < kFrameSyncMaxBits / 32 + 2; w += 32) sbuf[w] = 0u;
+    __syncwarp();
+    for (int q0 = 0; q0 < total; q0 += 32) {  // pack 32 bits per ballot
+        const int q = q0 + lane;
+        int v = 0;
+        if (q < total) v = q < ncarry ? st->carry[q] : b[q - ncarry];
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, v != 0);
+        if (lane == 0) sbuf[q0 >> 5] = word;
+    }
+    __syncwarp();
+    const int end_range = total >= 26 ? total - 26 : 0;  // idx < size-26: the last full window waits for more bits
+    for (int idx = lane; idx < end_range; idx += 32) stype[idx] = (int8_t)rds_block_type(bitbuf_window26(sbuf, idx));
+    __syncwarp();
+    if (lane == 0) {
+        uint64_t reg = st->reg;
+        int win[4] = {st->window[0], st->window[1], st->window[2], st->window[3]};
+        int nwin = st->nwindow;
+        int idx = 0, ng = 0;
+        while (idx < end_range) {
+            const int ty = stype[idx];
+            if (ty >= 0) {
+                if (ty != 3) {  // "Cp" matches but copies nothing (:370)
+                    const int bt = (ty == 4) ? 3 : ty;
+                    const uint64_t word = (uint64_t)((__brev(bitbuf_window26(sbuf, idx)) >> 16) & 0xFFFFu);
+                    const int shl = 48 - 16 * bt;
+                    reg = (reg & ~((uint64_t)0xFFFF << shl)) | (word << shl);
+                }
+                if (nwin == 4) { win[0] = win[1]; win[1] = win[2]; win[2] = win[3]; nwin = 3; }
+                win[nwin++] = ty;
+                if (nwin == 4 && win[0] == 0 && win[1] == 1 && win[2] == 2 && win[3] == 4) {
+                    if (ng < max_groups) groups[(size_t)s * groups_pitch + ng] = reg;
+                    ng++;
+                }
+                idx += 26;
+            } else {
+                idx += 1;
+            }
+        }
+        ngroups[s] = ng;
+        st->reg = reg;
+        st->window[0] = win[0]; st->window[1] = win[1]; st->window[2] = win[2]; st->window[3] = win[3];
+        st->nwindow = nwin;
+        int keep = total - idx;  // the unread tail is the carry (:398-399)
+        if (keep < 0) keep = 0;
+        if (keep > 64) keep = 64;  // cannot happen (keep <= 26); keeps the store in bounds whatever the input
+        for (int i = 0; i < keep; i++) st->carry[i] = (uint8_t)((sbuf[(idx + i) >> 5] >> ((idx + i) & 31)) & 1u);
+        st->ncarry = keep;
+    }
+}
+
 }  // namespace sdrb

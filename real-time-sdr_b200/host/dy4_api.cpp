@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
@@ -137,34 +138,36 @@ int cdr(int sps, const std::vector<float>& signal) {
     return off;
 }
 
-// The three functions below work on a few dozen ints per call.  Their batched form runs on the GPU inside
-// k_rds_backend (ballots for the Manchester pairing, one shifted XOR for the differential decode, 26-bit popcount
-// syndromes for the block check); the std::vector forms exist for API compatibility and stay on the host.
+// The bit-level stages run on the GPU as well: batch = 1 calls of sdrb_manchester_decode, sdrb_differential_decode and
+// sdrb_frame_sync (one warp per stream; the fused chain does the same work inside k_rds_backend).
 void manchester_decode(std::vector<int>& bits, const std::vector<int>& symbols, int& block_count, int& half_symbol, int& start) {
-    bits.clear();
-    const int n = (int)symbols.size();
-    if (start) bits.push_back(half_symbol);
-    if (block_count == 0) {  // pairing-phase estimate; unreachable from rds() (src/rds.cpp:135) but part of the function
-        int agree = 0;
-        for (int i = 0; i + 1 < n; i += 2) agree += symbols[i] ^ symbols[i + 1];
-        for (int i = 1; i + 1 < n; i += 2) agree -= symbols[i] ^ symbols[i + 1];
-        start = agree < 0 ? 1 : 0;
-    }
-    for (int i = start; i < n - 1; i += 2) bits.push_back(symbols[i]);
-    if (((unsigned)n - (unsigned)start) & 1u) {
-        half_symbol = symbols[n - 1];
-        start = 1;
-    } else {
-        start = 0;
-    }
+    const size_t n = symbols.size();
+    const int32_t nsym = (int32_t)n;
+    sdrb_manchester_state st{half_symbol, start};
+    DevBuf<int32_t> dsym(symbols.data(), n), dn(&nsym, 1), dbits(n / 2 + 2), dnb(1);
+    DevBuf<sdrb_manchester_state> dst(&st, 1);
+    ok(sdrb_manchester_decode(dsym.p, n ? n : 1, dn.p, block_count, dst.p, dbits.p, n / 2 + 2, dnb.p, 1, nullptr));
+    cu(cudaDeviceSynchronize());
+    int32_t nb = 0;
+    dnb.to_host(&nb, 1);
+    bits.assign((size_t)nb, 0);
+    dbits.to_host(bits.data(), (size_t)nb);
+    dst.to_host(&st, 1);
+    half_symbol = st.half_symbol;
+    start = st.start;
 }
 
 void differential_decode(std::vector<int>& decoded, const std::vector<int>& bits, int& last_bit, int& block_num) {
     if (bits.empty()) throw std::invalid_argument("differential_decode: empty input (undefined in the reference)");
+    const int32_t nb = (int32_t)bits.size();
+    int32_t last = last_bit;
+    DevBuf<int32_t> dbits(bits.data(), bits.size()), dn(&nb, 1), dlast(&last, 1), ddec(bits.size());
+    ok(sdrb_differential_decode(dbits.p, bits.size(), dn.p, block_num, dlast.p, ddec.p, bits.size(), 1, nullptr));
+    cu(cudaDeviceSynchronize());
     decoded.assign(bits.size(), 0);
-    decoded[0] = block_num == 0 ? bits[0] : (bits[0] ^ last_bit);
-    for (size_t i = 1; i < bits.size(); i++) decoded[i] = bits[i] ^ bits[i - 1];
-    last_bit = bits.back();
+    ddec.to_host(decoded.data(), bits.size());
+    dlast.to_host(&last, 1);
+    last_bit = last;
 }
 
 void parse(uint64_t bytes, uint64_t& chars, uint64_t& output, bool& first_time) {
@@ -204,15 +207,41 @@ void check_block(std::string& offset_type, std::vector<int>::iterator b, std::ve
 
 void start_frame_sync(unsigned int& idx, std::vector<int>& stream, std::vector<int>& carry, uint64_t& reg, uint64_t& chars, uint64_t& output,
                       bool& first_time, std::deque<std::string>& window) {
-    stream.insert(stream.begin(), carry.begin(), carry.end());
-    const unsigned int end_range = (unsigned int)stream.size() - 26u;  // unsigned like the reference: < 26 bits scans nothing sensible there
-    std::string kind;
-    if (stream.size() >= 26)
-        while (idx < end_range) {
-            check_block(kind, stream.begin() + idx, stream.begin() + idx + 26, reg, chars, output, first_time, window);
-            idx += kind != "None" ? 26 : 1;
-        }
-    carry.assign(stream.begin() + std::min<size_t>(idx, stream.size()), stream.end());
+    stream.insert(stream.begin(), carry.begin(), carry.end());  // the reference leaves the joined stream in its argument
+    if (stream.size() < 26 || idx >= stream.size() - 26) {      // nothing to scan (the reference's unsigned size-26 wraps for < 26 bits)
+        carry.assign(stream.begin() + std::min<size_t>(idx, stream.size()), stream.end());
+        return;
+    }
+    // the scan from `idx` of the joined stream = a scan from 0 of its tail, with no carried bits in the device state
+    const std::vector<int32_t> tail(stream.begin() + idx, stream.end());
+    if (tail.size() > 8128) throw std::invalid_argument("start_frame_sync: more than 8128 bits in one call");
+    sdrb_framesync_state st{};
+    st.reg = reg;
+    for (size_t i = 0; i < window.size() && i < 4; i++)
+        for (int t = 0; t < 5; t++)
+            if (window[i] == kOffsetNames[t]) st.window[i] = t;
+    st.nwindow = (int32_t)std::min<size_t>(window.size(), 4);
+    const int32_t nb = (int32_t)tail.size();
+    const int max_groups = nb / 104 + 2;  // a group is 4 x 26 bits
+    DevBuf<int32_t> dbits(tail.data(), tail.size()), dn(&nb, 1), dng(1);
+    DevBuf<sdrb_framesync_state> dst(&st, 1);
+    DevBuf<uint64_t> dgroups((size_t)max_groups);
+    ok(sdrb_frame_sync(dbits.p, tail.size(), dn.p, nb, dst.p, dgroups.p, (size_t)max_groups, dng.p, max_groups, 1, nullptr));
+    cu(cudaDeviceSynchronize());
+    int32_t ng = 0;
+    dng.to_host(&ng, 1);
+    std::vector<uint64_t> groups((size_t)std::min(ng, max_groups));
+    dgroups.to_host(groups.data(), groups.size());
+    dst.to_host(&st, 1);
+    for (uint64_t g : groups) {  // what check_block does at every A,B,C,D completion (src/rds_utilities.cpp:376-379)
+        parse(g, chars, output, first_time);
+        first_time = false;
+    }
+    reg = st.reg;
+    window.clear();
+    for (int i = 0; i < st.nwindow; i++) window.push_back(kOffsetNames[st.window[i]]);
+    idx = (unsigned int)(stream.size() - (size_t)st.ncarry);
+    carry.assign(stream.end() - st.ncarry, stream.end());
 }
 
 // ---- batched chain ------------------------------------------------------------------------------------------

@@ -124,3 +124,130 @@ def test_cdr(capi, oracle, torch):
     got = off.cpu().numpy()
     want = np.array([oracle.cdr(x[s], 39)[0] for s in range(S)])
     assert np.array_equal(got, want)
+
+
+def _run_bits_gpu(capi, torch, sym_blocks, block0):
+    """sdrb_manchester_decode + sdrb_differential_decode over consecutive blocks for a batch of streams.
+    sym_blocks[b][s] = symbols of stream s in block b.  Returns per stream (manchester, decoded, lens, state)."""
+    L = capi.lib()
+    S = len(sym_blocks[0])
+    pitch = max(max(len(x) for x in blk) for blk in sym_blocks) + 1
+    mst = torch.zeros(S * 2, dtype=torch.int32, device="cuda")
+    last = torch.zeros(S, dtype=torch.int32, device="cuda")
+    man = [[] for _ in range(S)]
+    dec = [[] for _ in range(S)]
+    lens = [[] for _ in range(S)]
+    bc = block0
+    for blk in sym_blocks:
+        sym = np.full((S, pitch), 7, np.int32)  # 7: a value a correct kernel never reads as a symbol
+        for s, x in enumerate(blk):
+            sym[s, :len(x)] = x
+        nsym = dev(torch, np.array([len(x) for x in blk], np.int32))
+        d_sym = dev(torch, sym)
+        bits = torch.full((S, pitch), -1, dtype=torch.int32, device="cuda")
+        out = torch.full((S, pitch), -1, dtype=torch.int32, device="cuda")
+        nb = torch.zeros(S, dtype=torch.int32, device="cuda")
+        capi.check(L.sdrb_manchester_decode(d_sym.data_ptr(), pitch, nsym.data_ptr(), bc, mst.data_ptr(), bits.data_ptr(), pitch,
+                                            nb.data_ptr(), S, None))
+        capi.check(L.sdrb_differential_decode(bits.data_ptr(), pitch, nb.data_ptr(), bc, last.data_ptr(), out.data_ptr(), pitch, S, None))
+        torch.cuda.synchronize()
+        nbh, bh, oh = nb.cpu().numpy(), bits.cpu().numpy(), out.cpu().numpy()
+        for s in range(S):
+            man[s].append(bh[s, :nbh[s]])
+            dec[s].append(oh[s, :nbh[s]])
+            lens[s].append(int(nbh[s]))
+            assert (bh[s, nbh[s]:] == -1).all() and (oh[s, nbh[s]:] == -1).all(), "wrote past the reported length"
+        bc += 1
+    msth, lasth = mst.cpu().numpy().reshape(S, 2), last.cpu().numpy()
+    return [(np.concatenate(man[s]), np.concatenate(dec[s]), np.array(lens[s], np.int32), (int(msth[s, 0]), int(msth[s, 1]), int(lasth[s])))
+            for s in range(S)]
+
+
+def test_manchester_differential_golden_and_batch(capi, oracle, torch):
+    """The reference's own vectors (tests/golden/ops.npz, made from src/rds_utilities.cpp:34-88), then a ragged random
+    batch against the oracle, including block_count == 0 (the pairing-phase estimate) and a one-symbol block."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ops.npz"))
+    cuts = np.cumsum(z["bits_lens"])[:-1]
+    blocks = np.split(z["bits_symbols"], cuts)
+    got = _run_bits_gpu(capi, torch, [[b, b] for b in blocks], block0=6)
+    for s in range(2):
+        man, dec, lens, state = got[s]
+        assert np.array_equal(man, z["bits_manchester"]) and np.array_equal(dec, z["bits_decoded"])
+        assert np.array_equal(lens, z["bits_out_lens"])
+        assert list(state) == [int(v) for v in z["bits_state"]]  # (half_symbol, start, last_bit)
+    rng = np.random.default_rng(5)
+    for block0 in (0, 3):
+        S, nblocks = 37, 6
+        sym_blocks = [[rng.integers(0, 2, int(rng.integers(4, 150))).astype(np.int32) for _ in range(S)] for _ in range(nblocks)]
+        sym_blocks[2][5] = np.array([1, 0, 1], np.int32)
+        got = _run_bits_gpu(capi, torch, sym_blocks, block0)
+        for s in range(S):
+            man, dec, lens, state = oracle.bits([sym_blocks[b][s] for b in range(nblocks)], block0=block0)
+            gm, gd, gl, gs = got[s]
+            assert np.array_equal(gm, man) and np.array_equal(gd, dec) and np.array_equal(gl, lens), (block0, s)
+            assert gs == tuple(state), (block0, s, gs, state)
+
+
+def test_frame_sync_golden_and_batch(capi, oracle, torch):
+    """sdrb_frame_sync on the reference's vectors (two calls of 545 bits: groups, carry, register), then many streams
+    with different bit streams and chunkings against the oracle."""
+    import os
+    L = capi.lib()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ops.npz"))
+
+    def run(chunks_per_stream, max_groups=32):
+        S = len(chunks_per_stream)
+        ncalls = len(chunks_per_stream[0])
+        st = torch.zeros(S * capi.FRAMESYNC_STATE_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        groups = [[] for _ in range(S)]
+        per_call = [[] for _ in range(S)]
+        for c in range(ncalls):
+            pitch = max(len(chunks_per_stream[s][c]) for s in range(S)) + 3
+            bits = np.zeros((S, pitch), np.int32)
+            for s in range(S):
+                bits[s, :len(chunks_per_stream[s][c])] = chunks_per_stream[s][c]
+            nb = dev(torch, np.array([len(chunks_per_stream[s][c]) for s in range(S)], np.int32))
+            d_bits = dev(torch, bits)
+            g = torch.zeros((S, max_groups), dtype=torch.int64, device="cuda")
+            ng = torch.zeros(S, dtype=torch.int32, device="cuda")
+            capi.check(L.sdrb_frame_sync(d_bits.data_ptr(), pitch, nb.data_ptr(), pitch, st.data_ptr(), g.data_ptr(), max_groups,
+                                         ng.data_ptr(), max_groups, S, None))
+            torch.cuda.synchronize()
+            gh, ngh = g.cpu().numpy().view(np.uint64), ng.cpu().numpy()
+            for s in range(S):
+                groups[s].extend(gh[s, :ngh[s]].tolist())
+                per_call[s].append(int(ngh[s]))
+        sth = st.cpu().numpy().view(capi.FRAMESYNC_STATE_DTYPE)
+        return groups, per_call, sth
+
+    cuts = np.cumsum(z["fs_lens"])[:-1]
+    chunks = np.split(z["fs_bits"], cuts)
+    groups, per_call, st = run([chunks, chunks])
+    for s in range(2):
+        assert np.array_equal(np.array(groups[s], np.uint64), z["fs_groups"])
+        assert np.array_equal(np.array(per_call[s], np.int32), z["fs_groups_per_call"])
+        assert int(st[s]["reg"]) == int(z["fs_state"][0])
+        assert np.array_equal(st[s]["carry"][: st[s]["ncarry"]].astype(np.int32), z["fs_carry"])
+
+    # many streams: the golden bit stream rotated by s bits (every alignment of the 26-bit grid), cut at random places,
+    # with bit errors in some streams, plus calls shorter than one window
+    rng = np.random.default_rng(9)
+    base = z["fs_bits"]
+    S = 41
+    per_stream = []
+    for s in range(S):
+        b = np.roll(base, s).copy()
+        if s % 3 == 2:
+            b[rng.integers(0, b.size, 12)] ^= 1
+        cuts = np.sort(rng.integers(0, b.size, 3))
+        if s == 7:
+            cuts = np.array([5, 20, 30])
+        per_stream.append([c.astype(np.int32) for c in np.split(b, cuts)])
+    groups, per_call, st = run(per_stream)
+    for s in range(S):
+        want_groups, want_calls, _, (reg, _, _), carry = oracle.frame_sync(per_stream[s])
+        assert np.array_equal(np.array(groups[s], np.uint64), want_groups), s
+        assert np.array_equal(np.array(per_call[s], np.int32), want_calls), s
+        assert int(st[s]["reg"]) == int(reg), s
+        assert np.array_equal(st[s]["carry"][: st[s]["ncarry"]].astype(np.int32), carry), s
