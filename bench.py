@@ -391,7 +391,10 @@ def main():
                 "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "algorithmic_bytes": alg_bytes.get(dom, 0),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6.65 TB/s",
                 "kernel_ms": {k: round(v, 4) for k, v in kernel_ms_timed.items()},
+                "hbm_gbs_per_kernel": {k: round(alg_bytes[k] / (v * 1e-3) / 1e9, 1) for k, v in kernel_ms.items() if k in alg_bytes and v > 0},
                 "kernel_ms_serialised": {k: round(v, 4) for k, v in kernel_ms.items()},
+                "hbm_note": "hbm_gbs_per_kernel: algorithmic bytes / serialised kernel time; every kernel is far below the HBM peak, the FIR "
+                            "kernels are graded against the no-FMA FP32 issue peak (fp32.per_kernel_frac), the slower of the two rooflines",
                 "timing": "kernel_ms: mean per launch over the timed region, CUDA events on each kernel's own stream (overlap mode, "
                           "kernels of neighbouring blocks run concurrently); kernel_ms_serialised: the same kernels one at a time",
                 "note": "the chain is FP32-issue / latency bound, not HBM bound (DESIGN.md section 5): see fp32"}

@@ -1,9 +1,9 @@
 """Per-instruction stall profile of k_pll's hot loop from an `ncu --set full --import-source on` capture.
 
-    python tools/pll_source_profile.py gpurun_out/pll_src.ncu-rep profiles/pll_hot_loop_r1f.txt [cycles_per_chunk]
+    python tools/pll_source_profile.py gpurun_out/prof_r1g.ncu-rep profiles/pll_hot_loop_r1g.txt [cycles_per_iteration]
 
 One warp runs per SM scheduler, so the warp-state samples of an instruction are the cycles the whole recurrence spent
-at it.  The summary lists the loop's stall reasons and, per region of the 4-sample chunk (found from the F2F that
+at it.  The summary lists the loop's stall reasons and, per region of the loop body (two 4-sample chunks since the loop is unrolled by two) (found from the F2F that
 widens the loop filter's phase once per sample), instructions and cycles (samples scaled to cycles_per_chunk, the
 measured 4 x cycles per sample of bench.py).
 """
@@ -16,8 +16,10 @@ import sys
 
 
 def main(rep, out, cycles_per_chunk):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:k_pll"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    rows = rows[starts[0]:starts[1]] if len(starts) > 1 else rows  # first captured launch of the kernel
     hdr = next(r for r in rows if "Source" in r and "# Samples" in r)
     idx = {h: i for i, h in enumerate(hdr)}
     data = [r for r in rows[rows.index(hdr) + 1:] if len(r) == len(hdr)]
@@ -30,8 +32,8 @@ def main(rep, out, cycles_per_chunk):
     k = cycles_per_chunk / total
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     agg = {h: sum(int(data[i][idx[h]]) for i in range(lo, hi + 1)) for h in stalls}
-    lines = [f"# k_pll hot loop: {len(hot)} instructions per chunk of 4 samples, {total} of {allk} warp-state samples ({total / allk:.1%} of the kernel)",
-             f"# samples scaled so that the loop is {cycles_per_chunk:.0f} cycles per chunk ({cycles_per_chunk / 4:.0f} per sample, bench.py)",
+    lines = [f"# k_pll hot loop: {len(hot)} instructions per loop iteration, {total} of {allk} warp-state samples ({total / allk:.1%} of the kernel)",
+             f"# samples scaled so that the loop is {cycles_per_chunk:.0f} cycles per iteration (bench.py: cycles per sample x samples per iteration)",
              "# stall reason, share of the loop's samples"]
     for h, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]:
         lines.append(f"{h}, {v / total:.3f}")
