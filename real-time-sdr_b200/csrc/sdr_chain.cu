@@ -75,6 +75,7 @@ struct sdrb_chain {
     int S = 0;
     int up = 1, down = 5;
     bool stereo = false, rds = false;
+    int pll_max_ctas = kPllMaxCtas;  // SMs given to k_pll (tuning knob: environment variable SDRB_PLL_MAX_CTAS)
     long long block = 0;  // index of the next block to process
     long long launches = 0;
     cudaStream_t stream = nullptr;  // the caller-visible stream: inputs are ordered on it, joins land on it
@@ -299,9 +300,12 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
             dim3 grid((S + T - 1) / T, loops);
             k_pll<T><<<grid, T, kPllSmemBytes, sp>>>(a);
         };
-        if ((S + 31) / 32 * loops <= kPllMaxCtas) launch(std::integral_constant<int, 32>{});
-        else if ((S + 63) / 64 * loops <= kPllMaxCtas) launch(std::integral_constant<int, 64>{});
-        else launch(std::integral_constant<int, 128>{});
+        // the smallest CTA that keeps the PLL on at most pll_max_ctas SMs (see kPllMaxCtas)
+        const int cap = c->pll_max_ctas;
+        if ((S + 31) / 32 * loops <= cap) launch(std::integral_constant<int, 32>{});
+        else if ((S + 63) / 64 * loops <= cap) launch(std::integral_constant<int, 64>{});
+        else if ((S + 127) / 128 * loops <= cap) launch(std::integral_constant<int, 128>{});
+        else launch(std::integral_constant<int, 256>{});
         if ((rc = check_launch(c, "k_pll", sp))) return rc;
     }
     if (ov) {
@@ -455,6 +459,17 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
     sdrb_chain* c = new sdrb_chain();
     c->cfg = *cfg;
     c->S = cfg->n_streams;
+    // SMs given to k_pll (measured, profiles/pll_sm_sweep_r1g.txt): one warp per SM on up to 64 SMs while the stations
+    // fit that way (<= 1024 stereo+RDS stations); beyond that the FIR kernels are the longer side of the step and get
+    // the SMs instead (32 for the PLL, more warps per CTA).
+    {
+        const int loops = cfg->type == 'r' ? 2 : 1;
+        c->pll_max_ctas = ((cfg->n_streams + 31) / 32 * loops <= kPllMaxCtas) ? kPllMaxCtas : kPllMaxCtas / 2;
+    }
+    if (const char* e = getenv("SDRB_PLL_MAX_CTAS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 148) c->pll_max_ctas = v;
+    }
     c->up = cfg->audio_upsample;
     c->down = cfg->audio_decim;
     c->stereo = cfg->type != 'm';
@@ -613,11 +628,12 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
             TRY(dalloc(c, (void**)&c->d_rclean, sizeof(float) * I.rds_block * S));
         }
     }
-    static_assert(pll_tile_bytes(kPllThreads) <= kPllSmemBytes, "PLL input ring must fit the reserved shared memory");
+    static_assert(pll_tile_bytes(256) <= kPllSmemBytes, "PLL input ring must fit the reserved shared memory");
     if (c->stereo) {
         TRYCU(cudaFuncSetAttribute(k_pll<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
         TRYCU(cudaFuncSetAttribute(k_pll<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
         TRYCU(cudaFuncSetAttribute(k_pll<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
+        TRYCU(cudaFuncSetAttribute(k_pll<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
     }
     if (c->rds) {
         const int rrc_tiles = (I.rds_block + kRrcTile - 1) / kRrcTile;

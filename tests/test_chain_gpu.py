@@ -313,3 +313,16 @@ def test_chain_at_large_nco_phase(capi, oracle, station_iq, n0):
     got = {k: np.concatenate(v) for k, v in acc.items()}
     got["pcm"] = np.concatenate(pcm)
     _assert_same(got, want, ["pcm"] + stages, f"n0={n0}")
+
+
+@pytest.mark.parametrize("cap,S", [("1", 70), ("4", 200), ("2", 33)])
+def test_pll_cta_sizes(capi, oracle, station_iq, monkeypatch, cap, S):
+    """k_pll with 256-, 128- and 64-thread CTAs (what large batches use; forced here through the SM-budget knob):
+    every stream still equals its own oracle run, including the partly filled last CTA."""
+    monkeypatch.setenv("SDRB_PLL_MAX_CTAS", cap)
+    nblocks = 8
+    iqs = [station_iq(k % 3, 0, nblocks) for k in range(S)]
+    got = run_cuda_chain(capi, 0, "r", iqs, nblocks)
+    wants = {k: oracle.chain(0, "r", station_iq(k, 0, nblocks)) for k in range(3)}
+    for s in range(S):
+        _assert_same(got[s], wants[s % 3], ["pcm"] + RDS_KEYS, f"cap {cap} stream {s}")
