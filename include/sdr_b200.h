@@ -150,6 +150,8 @@ typedef struct {
     int max_groups;    /* capacity of the per-block group record */
 } sdrb_chain_info;
 
+/* Tuning knob read here: the environment variable SDRB_PLL_MAX_CTAS (1..148) overrides the number of SMs the PLL
+ * kernel may occupy (default: 64 up to 1024 stereo+RDS stations, 32 beyond; results do not depend on it). */
 int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out);
 int sdrb_chain_destroy(sdrb_chain* c);
 int sdrb_chain_get_info(const sdrb_chain* c, sdrb_chain_info* info);
