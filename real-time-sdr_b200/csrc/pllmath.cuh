@@ -538,6 +538,13 @@ SDRB_HD void pll_cs(double sa, double cr_, double r, int kq, double& s0, double&
     sincos_quadrant(kq, r < 0.0 ? -sa : sa, cr_, s0, c0);
 }
 
+// cos_f out of line on the device: the callers below reach it about once per million arguments, and inlined at every
+// call site its double-double tier made k_mix five times larger than its hot path (instruction-cache misses)
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ float cos_f_rare(float t) { return cos_f(t); }
+#else
+inline float cos_f_rare(float t) { return cos_f(t); }
+#endif
 // cos_f with the leaner reduction: no rint, one acceptance test; anything doubtful goes to cos_f itself
 SDRB_HD float cos_lean_f(float t) {
     const double x = (double)t;
@@ -545,7 +552,7 @@ SDRB_HD float cos_lean_f(float t) {
     int q;
     const bool ok = sincos_reduce2(x, sa, cr_, r, q);
     pll_cs(sa, cr_, r, q, ds, dc);
-    if (!(fabs(x) < kReduceLimit) || !ok || near_float_boundary(dc)) return cos_f(t);
+    if (!(fabs(x) < kReduceLimit) || !ok || near_float_boundary(dc)) return cos_f_rare(t);
     return (float)dc;
 }
 
