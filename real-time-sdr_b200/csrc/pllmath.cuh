@@ -189,20 +189,28 @@ constexpr double kReduceLimit = 3.0e9;  // |x| below this: k < 2^31, exact Cody-
 // C1..C6, approximation error below 2^-58), evaluated Estrin-style so the dependent depth is z, z^2, z^4 and two fmas.
 // Far inside the 2^-45 the callers allow before they consult the double-double tier.
 SDRB_HD void sincos_poly2(double r, double rs, double& sr, double& cr_) {  // sr = sin(rs), rs = r or |r|
+    // Dependent depth 4 (z; z^2, the coefficient pairs, r z, 1 - z/2; three partial sums; the result): one level less
+    // than the plain Estrin form, and every level is 8 cycles of the PLL recurrence.
     const double z = dmul(r, r);
-    const double z2 = dmul(z, z), z4 = dmul(z2, z2);
-    // sin r = r + r z (S1 + S2 z + S3 z^2 + S4 z^3 + S5 z^4 + S6 z^5)
+    const double z2 = dmul(z, z);
+    // sin r = r + r z (S1 + S2 z) + (r z z^2) ((S3 + S4 z) + z^2 (S5 + S6 z))
     const double s12 = dfma(K(kS2), z, K(kS1));
     const double s34 = dfma(K(kS4), z, K(kS3));
     const double s56 = dfma(K(kS6), z, K(kS5));
-    const double sp = dfma(z4, s56, dfma(z2, s34, s12));
-    sr = dfma(dmul(rs, z), sp, rs);
-    // cos r = 1 - z/2 + z^2 (C1 + C2 z + C3 z^2 + C4 z^3 + C5 z^4 + C6 z^5)
+    const double rz = dmul(rs, z);
+    const double sA = dfma(rz, s12, rs);
+    const double sB = dmul(rz, z2);
+    const double sC = dfma(z2, s56, s34);
+    sr = dfma(sB, sC, sA);
+    // cos r = (1 - z/2) + z^2 (C1 + C2 z) + z^4 ((C3 + C4 z) + z^2 (C5 + C6 z))
     const double c12 = dfma(K(kC2), z, K(kC1));
     const double c34 = dfma(K(kC4), z, K(kC3));
     const double c56 = dfma(K(kC6), z, K(kC5));
-    const double cp = dfma(z4, c56, dfma(z2, c34, c12));
-    cr_ = dfma(z2, cp, dfma(-0.5, z, 1.0));
+    const double ch = dfma(-0.5, z, 1.0);
+    const double cA = dfma(z2, c12, ch);
+    const double z4 = dmul(z2, z2);
+    const double cC = dfma(z2, c56, c34);
+    cr_ = dfma(z4, cC, cA);
 }
 SDRB_HD void sincos_poly(double r, double& sr, double& cr_) { sincos_poly2(r, r, sr, cr_); }
 SDRB_HD double flip_sign_if(double v, unsigned flip) {  // exact negation by a sign-bit XOR (one integer op on the chain)
