@@ -528,7 +528,11 @@ __device__ __forceinline__ double pll_recip(float v) {
 constexpr int kPllTileChunks = 8;  // 32 steps per staged tile
 
 constexpr int kPllTileRow = 4 * kPllTileChunks + 4;
-constexpr size_t pll_tile_bytes(int threads) { return sizeof(float) * 3 * threads * kPllTileRow; }
+#ifndef SDRB_PLL_RING
+#define SDRB_PLL_RING 3
+#endif
+constexpr int kPllRing = SDRB_PLL_RING;  // tiles in the input ring; kPllRing - 1 of them are in flight ahead of the loop
+constexpr size_t pll_tile_bytes(int threads) { return sizeof(float) * kPllRing * threads * kPllTileRow; }
 // The launch asks for (nearly) all of an SM's shared memory, far more than the input ring needs: no other CTA then fits
 // on that SM, so in overlap mode the FIR kernels of the neighbouring blocks cannot steal issue slots from the
 // latency-bound warps.
@@ -571,7 +575,7 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
     auto issue_tile = [&](int t) {
         if (t < ntiles) {
             const float* src = x + t * (4 * kPllTileChunks);
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile[t % 3][lane][0]);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tile[t % kPllRing][lane][0]);
 #pragma unroll
             for (int j = 0; j < kPllTileChunks; j++)
                 if (t * kPllTileChunks + j < nc)
@@ -579,8 +583,8 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    issue_tile(0);
-    issue_tile(1);
+#pragma unroll
+    for (int t0 = 0; t0 < kPllRing - 1; t0++) issue_tile(t0);
     float4 vc = make_float4(1.f, 1.f, 1.f, 1.f);
     double q0 = 1.0, q1 = 1.0, q2 = 1.0, q3 = 1.0;
     float4* o4 = reinterpret_cast<float4*>(out);
@@ -590,11 +594,11 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
     // body outgrows the instruction cache and the kernel slows down by 10-30 %).
     int g = 0;
     for (int t = 0; t < ntiles; t++) {
-        issue_tile(t + 2);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");  // tiles t and t+1 have landed
+        issue_tile(t + kPllRing - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kPllRing - 2) : "memory");  // tiles t and t+1 have landed
         __syncwarp();  // a lane only ever reads the row it filled itself
-        const float4* cur = reinterpret_cast<const float4*>(&tile[t % 3][lane][0]);
-        const float4* nxt = reinterpret_cast<const float4*>(&tile[(t + 1) % 3][lane][0]);
+        const float4* cur = reinterpret_cast<const float4*>(&tile[t % kPllRing][lane][0]);
+        const float4* nxt = reinterpret_cast<const float4*>(&tile[(t + 1) % kPllRing][lane][0]);
         if (t == 0) {
             vc = cur[0];
             q0 = pll_recip(vc.x); q1 = pll_recip(vc.y); q2 = pll_recip(vc.z); q3 = pll_recip(vc.w);
