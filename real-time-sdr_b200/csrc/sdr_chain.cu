@@ -331,7 +331,8 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
         dim3 grid((n_if + 1 + 256 * kMixPer - 1) / (256 * kMixPer), S);
         // k_mix needs no shared memory, which would let its CTAs slip into the few KB the PLL kernel leaves free on the SMs
         // it reserves; asking for 8 KB keeps them off those SMs (the other kernels of the chain already use more).
-        k_mix<<<grid, 256, 8192, sb>>>(a);
+        if (c->rds && !keep) k_mix<true><<<grid, 256, 8192, sb>>>(a);
+        else k_mix<false><<<grid, 256, 8192, sb>>>(a);
         if ((rc = check_launch(c, "k_mix", sb))) return rc;
     }
     {

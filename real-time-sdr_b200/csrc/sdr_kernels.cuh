@@ -655,43 +655,62 @@ struct MixArgs {
 
 constexpr int kMixPer = 4;  // consecutive samples per thread: all loads first, then the cosines
 
+// One sample of the generic (bounds- and option-checked) form: the tail of a row and the stage-dumping parity runs.
+__device__ __forceinline__ void mix_one_checked(const MixArgs& a, int s, int i, bool rds) {
+    const bool in_blk = i < a.n;
+    if (a.do_stereo) {
+        const float th = a.trig19[(size_t)s * a.trig19_pitch + i - 1];
+        const float car = cr::cos_lean_f(__fadd_rn(__fmul_rn(th, a.scale19), a.adjust19));
+        if (a.carrier_out) a.carrier_out[(size_t)s * (a.n + 1) + i] = car;
+        if (in_blk) {
+            const float band = a.band[(size_t)s * a.band_pitch + i];
+            ring_store(a.stereo_dc, s, i, __double2float_rn(__dmul_rn(__dmul_rn(2.0, (double)band), (double)car)));
+        }
+    }
+    if (rds) {
+        const float th = a.trig114[(size_t)s * a.trig114_pitch + i - 1];
+        const float ip = cr::cos_lean_f(__fadd_rn(__fmul_rn(th, a.scale114), a.adjust114));
+        if (a.ipll_out) a.ipll_out[(size_t)s * (a.n + 1) + i] = ip;
+        if (in_blk) {
+            // the all-pass "delay" FIR (src/rds.cpp:122): 0 + 1*x[i-50] + 0*... == 0.0f + x[i-50]
+            const float d = __fadd_rn(0.0f, a.rds_band[(size_t)s * a.rds_band_pitch + i - 50]);
+            if (a.delay_out) a.delay_out[(size_t)s * a.n + i] = d;
+            ring_store(a.rds_dc, s, i, __fmul_rn(__fmul_rn(2.0f, d), ip));
+        }
+    }
+}
+
+// FAST: no stage dumps are requested and both mixers run (the production configuration): a thread whose kMixPer
+// samples lie inside the block and before the halo tail takes a path without a single bounds or option test.
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_mix(const MixArgs a) {
     const int s = blockIdx.y;
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * kMixPer;
     if (i0 > a.n) return;
-    float th19[kMixPer], band[kMixPer], th114[kMixPer], rb[kMixPer];
     const bool rds = a.rds_band != nullptr;
+    if (FAST && i0 + kMixPer <= a.n - max(a.stereo_dc.halo, a.rds_dc.halo)) {
+        const float* t19 = a.trig19 + (size_t)s * a.trig19_pitch + i0 - 1;
+        const float* bd = a.band + (size_t)s * a.band_pitch + i0;
+        const float* t114 = a.trig114 + (size_t)s * a.trig114_pitch + i0 - 1;
+        const float* rb = a.rds_band + (size_t)s * a.rds_band_pitch + i0 - 50;
+        float th19[kMixPer], band[kMixPer], th114[kMixPer], rbd[kMixPer];
 #pragma unroll
-    for (int j = 0; j < kMixPer; j++) {
-        const int i = i0 + j;
-        const bool in_car = i <= a.n, in_blk = i < a.n;
-        th19[j] = (a.do_stereo && in_car) ? a.trig19[(size_t)s * a.trig19_pitch + i - 1] : 0.0f;
-        band[j] = (a.do_stereo && in_blk) ? a.band[(size_t)s * a.band_pitch + i] : 0.0f;
-        th114[j] = (rds && in_car) ? a.trig114[(size_t)s * a.trig114_pitch + i - 1] : 0.0f;
-        rb[j] = (rds && in_blk) ? a.rds_band[(size_t)s * a.rds_band_pitch + i - 50] : 0.0f;
+        for (int j = 0; j < kMixPer; j++) { th19[j] = t19[j]; band[j] = bd[j]; th114[j] = t114[j]; rbd[j] = rb[j]; }
+        float* sdc = a.stereo_dc.cur + (size_t)s * a.stereo_dc.pitch + i0;
+        float* rdc = a.rds_dc.cur + (size_t)s * a.rds_dc.pitch + i0;
+#pragma unroll
+        for (int j = 0; j < kMixPer; j++) {
+            const float car = cr::cos_lean_f(__fadd_rn(__fmul_rn(th19[j], a.scale19), a.adjust19));
+            sdc[j] = __double2float_rn(__dmul_rn(__dmul_rn(2.0, (double)band[j]), (double)car));
+            const float ip = cr::cos_lean_f(__fadd_rn(__fmul_rn(th114[j], a.scale114), a.adjust114));
+            rdc[j] = __fmul_rn(__fmul_rn(2.0f, __fadd_rn(0.0f, rbd[j])), ip);
+        }
+        return;
     }
-#pragma unroll
     for (int j = 0; j < kMixPer; j++) {
         const int i = i0 + j;
         if (i > a.n) break;
-        if (a.do_stereo) {
-            const float car = cr::cos_lean_f(__fadd_rn(__fmul_rn(th19[j], a.scale19), a.adjust19));
-            if (a.carrier_out) a.carrier_out[(size_t)s * (a.n + 1) + i] = car;
-            if (i < a.n) {
-                const float v = __double2float_rn(__dmul_rn(__dmul_rn(2.0, (double)band[j]), (double)car));
-                ring_store(a.stereo_dc, s, i, v);
-            }
-        }
-        if (rds) {
-            const float ip = cr::cos_lean_f(__fadd_rn(__fmul_rn(th114[j], a.scale114), a.adjust114));
-            if (a.ipll_out) a.ipll_out[(size_t)s * (a.n + 1) + i] = ip;
-            if (i < a.n) {
-                // the all-pass "delay" FIR (src/rds.cpp:122): 0 + 1*x[i-50] + 0*... == 0.0f + x[i-50]
-                const float d = __fadd_rn(0.0f, rb[j]);
-                if (a.delay_out) a.delay_out[(size_t)s * a.n + i] = d;
-                ring_store(a.rds_dc, s, i, __fmul_rn(__fmul_rn(2.0f, d), ip));
-            }
-        }
+        mix_one_checked(a, s, i, rds);
     }
 }
 
