@@ -426,6 +426,26 @@ __global__ void __launch_bounds__(32 * kBankWarps) k_fir_bank(const __grid_const
     const float* xr = a.x + (size_t)s * a.x_pitch + n0 - kState;
     float* fE = reinterpret_cast<float*>(sE[warp]);
     float* fO = reinterpret_cast<float*>(sO[warp]);
+    // Staging.  Inside the block (every tile but the last of a row) a lane loads one even-aligned pair per step, which
+    // is E[m] as it stands, and gets x[2m+2] for O[m] from its neighbour by shuffle: 5 instructions per sample instead
+    // of 17 for the element-wise form below (bounds test, two index computations with a division, two scalar stores).
+    if (n0 + kBankTile + 2 <= a.n && (((uintptr_t)xr & 7u) == 0)) {
+        static_assert(NS % 2 == 0, "pairs");
+        const float2* xp = reinterpret_cast<const float2*>(xr);
+        for (int m0 = 0; m0 < NP; m0 += 32) {
+            const int m = m0 + lane;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (m < NP) v = xp[m];  // m = NP-1 reads x[NS], x[NS+1]: inside the block by the test above
+            if (SQUARE) v = make_float2(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y));
+            float nx = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
+            if (lane == 31 && m + 1 < NP) { nx = xr[2 * m + 2]; if (SQUARE) nx = __fmul_rn(nx, nx); }
+            if (m < NP) {
+                const int pos = m + m / HP;
+                sE[warp][pos] = v;
+                sO[warp][pos] = make_float2(v.y, nx);
+            }
+        }
+    } else
     for (int u = lane; u < NS + 2; u += 32) {
         float v = (u < NS && n0 - kState + u < a.n) ? xr[u] : 0.0f;
         if (SQUARE) v = __fmul_rn(v, v);
@@ -443,6 +463,23 @@ __global__ void __launch_bounds__(32 * kBankWarps) k_fir_bank(const __grid_const
 #pragma unroll
         for (int p = 0; p < HP; p++) acc[f][p] = make_float2(0.0f, 0.0f);
     fir_bank_core<NF, kBankR>(&sE[warp][(HP + 1) * lane], &sO[warp][(HP + 1) * lane], a.taps, acc);
+    // A tile that ends before the part of the block that is also the next block's halo (all but the last one or two
+    // tiles of a row) stores pairs directly: no bounds test, no halo test, one 64-bit store per pair.
+    int hmax = 0;
+#pragma unroll
+    for (int f = 0; f < NF; f++) hmax = max(hmax, a.y[f].halo);
+    bool fast = n0 + kBankTile <= a.n - hmax;
+#pragma unroll
+    for (int f = 0; f < NF; f++) fast = fast && (((uintptr_t)(a.y[f].cur + (size_t)s * a.y[f].pitch + n0) & 7u) == 0);
+    if (fast) {
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            float2* row = reinterpret_cast<float2*>(a.y[f].cur + (size_t)s * a.y[f].pitch + n0 + kBankR * lane);
+#pragma unroll
+            for (int p = 0; p < HP; p++) row[p] = acc[f][p];
+        }
+        return;
+    }
 #pragma unroll
     for (int f = 0; f < NF; f++)
 #pragma unroll
@@ -476,6 +513,22 @@ __global__ void __launch_bounds__(32 * kBankWarps) k_fir_bank_scalar(const __gri
 #pragma unroll
         for (int j = 0; j < kBankR; j++) acc[f][j] = 0.0f;
     fir_bank_core_scalar<NF, kBankR>(&sx[warp][(kBankR + 1) * lane], a.taps, acc);
+    int hmax = 0;
+#pragma unroll
+    for (int f = 0; f < NF; f++) hmax = max(hmax, a.y[f].halo);
+    bool fast = n0 + kBankTile <= a.n - hmax;  // see k_fir_bank
+#pragma unroll
+    for (int f = 0; f < NF; f++) fast = fast && (((uintptr_t)(a.y[f].cur + (size_t)s * a.y[f].pitch + n0) & 15u) == 0);
+    if (fast) {
+        static_assert(kBankR % 4 == 0, "float4 stores");
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            float4* row = reinterpret_cast<float4*>(a.y[f].cur + (size_t)s * a.y[f].pitch + n0 + kBankR * lane);
+#pragma unroll
+            for (int j = 0; j < kBankR; j += 4) row[j / 4] = make_float4(acc[f][j], acc[f][j + 1], acc[f][j + 2], acc[f][j + 3]);
+        }
+        return;
+    }
 #pragma unroll
     for (int f = 0; f < NF; f++)
 #pragma unroll
