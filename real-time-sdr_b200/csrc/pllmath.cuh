@@ -149,6 +149,26 @@ SDRB_HD double K(PllConst i) {
 #endif
 }
 
+// The same constants pinned in registers for the batched PLL kernel: left to itself the compiler re-reads the
+// constant bank inside the loop (28 LDC per 8 samples, each an issue slot of an in-order warp that has none to spare).
+// They are read once through a volatile global load, which cannot be rematerialised.
+struct PllK {
+    double v[15];
+};
+#if defined(__CUDACC__)
+__device__ double g_pll_consts[15] = SDRB_PLL_CONSTS;
+#endif
+SDRB_HD void pll_k_load(PllK& kk) {
+#pragma unroll
+    for (int i = 0; i < 15; i++) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(kk.v[i]) : "l"(&g_pll_consts[i]));
+#else
+        kk.v[i] = h_pll_consts[i];
+#endif
+    }
+}
+
 // ---- float rounding boundary test ----
 // A double v rounds to float by dropping its low 29 mantissa bits; the boundary (tie) pattern of those
 // bits is 0x10000000.  `true` means: v is so close to a boundary (or so small that the float is
@@ -213,6 +233,27 @@ SDRB_HD void sincos_poly2(double r, double rs, double& sr, double& cr_) {  // sr
     cr_ = dfma(z4, cC, cA);
 }
 SDRB_HD void sincos_poly(double r, double& sr, double& cr_) { sincos_poly2(r, r, sr, cr_); }
+// sincos_poly2 with the coefficients from registers (PllK), same operations in the same order
+SDRB_HD void sincos_poly2k(double r, double rs, double& sr, double& cr_, const PllK& kk) {
+    const double z = dmul(r, r);
+    const double z2 = dmul(z, z);
+    const double s12 = dfma(kk.v[kS2], z, kk.v[kS1]);
+    const double s34 = dfma(kk.v[kS4], z, kk.v[kS3]);
+    const double s56 = dfma(kk.v[kS6], z, kk.v[kS5]);
+    const double rz = dmul(rs, z);
+    const double sA = dfma(rz, s12, rs);
+    const double sB = dmul(rz, z2);
+    const double sC = dfma(z2, s56, s34);
+    sr = dfma(sB, sC, sA);
+    const double c12 = dfma(kk.v[kC2], z, kk.v[kC1]);
+    const double c34 = dfma(kk.v[kC4], z, kk.v[kC3]);
+    const double c56 = dfma(kk.v[kC6], z, kk.v[kC5]);
+    const double ch = dfma(-0.5, z, 1.0);
+    const double cA = dfma(z2, c12, ch);
+    const double z4 = dmul(z2, z2);
+    const double cC = dfma(z2, c56, c34);
+    cr_ = dfma(z4, cC, cA);
+}
 SDRB_HD double flip_sign_if(double v, unsigned flip) {  // exact negation by a sign-bit XOR (one integer op on the chain)
 #if defined(__CUDA_ARCH__)
     return __hiloint2double(__double2hiint(v) ^ (int)(flip << 31), __double2loint(v));
@@ -683,15 +724,17 @@ SDRB_HD unsigned ambig_abs(double v) {  // near_float_boundary_abs, branch-free
     return (unsigned)((E - (1023u - 17u)) > 18u) | (unsigned)(off <= 2u * thr);
 }
 
-SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, unsigned& bad) {
+SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, const PllK& kk, unsigned& bad) {
     // -- beside the chain: needs only `in` and the previous step's reduction --
+    // rin is the raw reciprocal approximation: `in` outside 2^-90 <= |in| < 2^90 (zero, subnormal, inf, NaN too) rejects
+    bad |= (unsigned)(((fbits(in) & 0x7FFFFFFFu) - 0x12800000u) >= (0x6C800000u - 0x12800000u));
     const uint32_t rhi = dhi(f.r);
     const uint32_t rs = rhi & 0x80000000u;  // r < 0
     const unsigned m = ((unsigned)f.kq + ((fbits(in) >> 31) << 1)) & 3u;
     // -theta (+pi) = -r - m*pi/2 in (-pi, pi]:  mm = 0, -1, -+2 (by the sign of r), +1 for m = 0, 1, 2, 3
     const uint32_t mmhi = (m & 1u) ? ((m & 2u) ? 0x3FF00000u : 0xBFF00000u) : ((m & 2u) ? (0xC0000000u ^ rs) : 0u);
     const double mm = mkd(mmhi, 0u);
-    const double base = dfma(mm, K(kKPio2M), dfma(mm, K(kKPio2H), -f.r));
+    const double base = dfma(mm, kk.v[kKPio2M], dfma(mm, kk.v[kKPio2H], -f.r));
     const uint32_t bh = dhi(base);
     const uint32_t Ke = d2f_K(bh);
     const double ars = mkd(dhi(rin) ^ rs, dlo(rin));  // (-1)^[r<0] / |in|
@@ -720,13 +763,13 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     // quarter-turn reduction and polynomials (sincos_reduce2, inlined so that its test joins `bad`).  The quadrant
     // count must come from xd, not td: once the phase passes 2^22 the float grid is coarser than pi/4, td and xd can
     // be a radian apart, and a count taken from td would leave |r| far outside the range of the kernels below.
-    const double tm = dfma(xd, K(kK2OverPi), kMagicRint);
+    const double tm = dfma(xd, kk.v[kK2OverPi], kMagicRint);
     const double kd = dadd(tm, -kMagicRint);
     const int q = (int)dlo(tm) & 3;
-    const double r = dfma(-kd, K(kKPio2M), dfma(-kd, K(kKPio2H), xd));
+    const double r = dfma(-kd, kk.v[kKPio2M], dfma(-kd, kk.v[kKPio2H], xd));
     const uint32_t rah = dhi(r) & 0x7FFFFFFFu;
     double sa, cr_;
-    sincos_poly2(r, mkd(rah, dlo(r)), sa, cr_);  // |r| joins only at the last fma of the sine
+    sincos_poly2k(r, mkd(rah, dlo(r)), sa, cr_, kk);  // |r| joins only at the last fma of the sine
     // -- the tests --
     // e: NaN/inf (an out-of-range `in`), the wrap (|e| < pi), the linearisation (|e - base| = |u/in| < 2^-22), the
     // float rounding of e, and base so close to +-2 that e and base could differ in the nibble d2f_known was told
@@ -751,22 +794,22 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
 // the careful repeat of four steps (rare: kept out of line on the device so the hot loop stays small)
 SDRB_RARE void pll_redo4(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, PllFast& f,
                          const PllCoef& k, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3) {
-    t0 = pll_step_fast(i0, r0, f, k, tab);
-    t1 = pll_step_fast(i1, r1, f, k, tab);
-    t2 = pll_step_fast(i2, r2, f, k, tab);
-    t3 = pll_step_fast(i3, r3, f, k, tab);
+    t0 = pll_step_fast(i0, pll_guard_recip(i0, r0), f, k, tab);  // r0..r3 are raw reciprocals: guarded here
+    t1 = pll_step_fast(i1, pll_guard_recip(i1, r1), f, k, tab);
+    t2 = pll_step_fast(i2, pll_guard_recip(i2, r2), f, k, tab);
+    t3 = pll_step_fast(i3, pll_guard_recip(i3, r3), f, k, tab);
 }
 
 // Four consecutive samples: speculative run, verified once; the careful path only on failure.
-// r0..r3 = pll_guard_recip of the samples.
+// r0..r3 = raw reciprocal approximations 1/|in| of the samples (any value for an `in` the step rejects).
 SDRB_HD void pll_chunk4(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, PllFast& f,
-                        const PllCoef& k, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3) {
+                        const PllCoef& k, const PllK& kk, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3) {
     const PllFast saved = f;
     unsigned bad = f.generic_next ? 1u : 0u;
-    t0 = pll_step_spec(i0, r0, f, k, bad);
-    t1 = pll_step_spec(i1, r1, f, k, bad);
-    t2 = pll_step_spec(i2, r2, f, k, bad);
-    t3 = pll_step_spec(i3, r3, f, k, bad);
+    t0 = pll_step_spec(i0, r0, f, k, kk, bad);
+    t1 = pll_step_spec(i1, r1, f, k, kk, bad);
+    t2 = pll_step_spec(i2, r2, f, k, kk, bad);
+    t3 = pll_step_spec(i3, r3, f, k, kk, bad);
     if (bad) {  // only here does the state have to live in addressable memory (the out-of-line call)
         PllFast again = saved;
         float a0, a1, a2, a3;

@@ -570,12 +570,12 @@ constexpr int kPllThreads = 128;  // largest CTA; also the block size of the gen
 constexpr int kPllMaxCtas = 64;
 
 // 1/v for the rotated phase detector: w = u * (1/in) is a <= 2^-22 rad correction whose absolute error may be 2^-45,
-// so a relative 2^-23 is enough: the FP32 reciprocal approximation (MUFU.RCP, 1 ulp) widened to double.  v = 0 or
-// subnormal gives inf, which the step's |w| test turns into the general path.
+// so a relative 2^-23 is enough: the FP32 reciprocal approximation (MUFU.RCP, 1 ulp) widened to double, unguarded:
+// the speculative step itself rejects samples outside 2^-90 <= |in| < 2^90, and the careful path guards its own.
 __device__ __forceinline__ double pll_recip(float v) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fabsf(v)));
-    return cr::pll_guard_recip(v, (double)r);
+    return (double)r;
 }
 
 constexpr int kPllTileChunks = 8;  // 32 steps per staged tile
@@ -641,6 +641,8 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
     float4 vc = make_float4(1.f, 1.f, 1.f, 1.f);
     double q0 = 1.0, q1 = 1.0, q2 = 1.0, q3 = 1.0;
     float4* o4 = reinterpret_cast<float4*>(out);
+    cr::PllK kk;
+    cr::pll_k_load(kk);
     // Loop shape (measured, profiles/README.md): tiles outside and chunks inside, so the common path has no branch
     // around the tile staging (a taken branch costs ~16 cycles of instruction fetch on a warp that has its scheduler to
     // itself); the chunk loop unrolled by two (half the loop branches and state-rotation moves; by four or more the
@@ -666,14 +668,14 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
             const float4 vn = *(j + 1 < kPllTileChunks ? cur + j + 1 : nxt);
             const double p0 = pll_recip(vn.x), p1 = pll_recip(vn.y), p2 = pll_recip(vn.z), p3 = pll_recip(vn.w);
             float4 o;
-            cr::pll_chunk4(vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, f, k, tab, o.x, o.y, o.z, o.w);
+            cr::pll_chunk4(vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, f, k, kk, tab, o.x, o.y, o.z, o.w);
             o4[g] = o;
             vc = vn;
             q0 = p0; q1 = p1; q2 = p2; q3 = p3;
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_fast(x[i], pll_recip(x[i]), f, k, tab);
+    for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_fast(x[i], cr::pll_guard_recip(x[i], pll_recip(x[i])), f, k, tab);
     // tail -> halo of the next slot
     float* nh = lp.trig.nxt + (size_t)s * lp.trig.pitch;
     for (int b = 1; b <= lp.trig.halo && b <= a.n; b++) nh[-b] = out[a.n - b];

@@ -125,16 +125,18 @@ void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, flo
     pll_fast_load(f, st, k);
     out[0] = out[n];
     uint64_t gen_atan = 0, gen_sc = 0;
+    PllK kk;
+    pll_k_load(kk);
     int i = 0;
     for (; i + 4 <= n; i += 4) {  // the kernel's chunking: 4 speculative steps, verified once
         float c[4] = {in[i], in[i + 1], in[i + 2], in[i + 3]}, th[4];
-        auto recip = [](float v) { return pll_guard_recip(v, 1.0 / fabs((double)v)); };  // device: rcp.approx.ftz of |v|
+        auto recip = [](float v) { return 1.0 / fabs((double)v); };  // device: rcp.approx.ftz of |v|; the step itself rejects out-of-range samples
         double r[4] = {recip(c[0]), recip(c[1]), recip(c[2]), recip(c[3])};
         PllFast probe = f;
         unsigned bad = f.generic_next ? 1u : 0u;
-        for (int j = 0; j < 4; j++) pll_step_spec(c[j], r[j], probe, k, bad);
+        for (int j = 0; j < 4; j++) pll_step_spec(c[j], r[j], probe, k, kk, bad);
         if (bad) gen_atan++;  // chunks that needed the careful path
-        pll_chunk4(c[0], c[1], c[2], c[3], r[0], r[1], r[2], r[3], f, k, kTab, th[0], th[1], th[2], th[3]);
+        pll_chunk4(c[0], c[1], c[2], c[3], r[0], r[1], r[2], r[3], f, k, kk, kTab, th[0], th[1], th[2], th[3]);
         if (f.generic_next) gen_sc++;
         for (int j = 0; j < 4; j++) out[i + j + 1] = nco_out(th[j], k);
     }
