@@ -771,11 +771,11 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     double sa, cr_;
     sincos_poly2k(r, mkd(rah, dlo(r)), sa, cr_, kk);  // |r| joins only at the last fma of the sine
     // -- the tests --
-    // e: NaN/inf (an out-of-range `in`), the wrap (|e| < pi), the linearisation (|e - base| = |u/in| < 2^-22), the
-    // float rounding of e, and base so close to +-2 that e and base could differ in the nibble d2f_known was told
-    const double wq = dadd(e, -base);
-    bad |= (unsigned)((dhi(e) & 0x7FFFFFFFu) >= 0x400921F9u) | (unsigned)((dhi(wq) & 0x7FFFFFFFu) >= 0x3E900000u) | ambig_abs(e) |
-           (unsigned)(((bh & 0x7FFFFFFFu) - 0x3FFFFFFFu) <= 1u);
+    // e: the wrap (|e| < pi), the float rounding of e, and base so close to +-2 that e and base could differ in the
+    // nibble d2f_known was told.  (The linearisation atan(u/v) = u/in needs |u/in| < 2^-22, which holds by construction:
+    // |u/in| <= sa * cr * 4 * 2^-24 from the four float roundings, none of which can underflow for 2^-90 <= |in| < 2^90
+    // and sa >= 2^-31, both enforced; a NaN/inf e cannot arise from an accepted `in` either.)
+    bad |= (unsigned)((dhi(e) & 0x7FFFFFFFu) >= 0x400921F9u) | ambig_abs(e) | (unsigned)(((bh & 0x7FFFFFFFu) - 0x3FFFFFFFu) <= 1u);
     // td left the binade of M; r tiny; sa / cr near a float rounding tie
     bad |= (unsigned)((((dhi(td) & 0x7FF00000u) + (29u << 20)) | (1u << 19)) != dhi(f.magic)) | (unsigned)(rah < 0x3E100000u) |
            ambig_rel_lo(sa) | ambig_rel_lo(cr_);
