@@ -1004,6 +1004,7 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
                 int n = (q0 + qq) * kRdsUp + tp;
                 off[qq] = (n < n_out) ? kRdsDown * (q0 + qq) + base + kState : kState;
             }
+#pragma unroll 8  // eight tap loads in flight ahead of their MACs: 0.117 -> 0.086 ms for the kernel (4: 0.111, 16: 0.086)
             for (int j = 0; j < kTaps; j++) {
                 const float hj = __ldg(a.taps_perm + j * 256 + t);
 #pragma unroll
