@@ -171,9 +171,17 @@ int sdrb_chain_sync(sdrb_chain* c);
  * 0: every kernel of a block is issued on the chain's stream, in order.
  * 1: the front end of block b+1 (RF front end, band filters) runs concurrently with the PLL and back end of block b
  *    on internal CUDA streams chained by events (the rings are three slots deep for this), and process_host copies on
- *    a copy-engine stream.  The input buffer of a block is then read asynchronously with respect to the chain's
- *    stream: keep it unchanged until sdrb_chain_join / _sync / a read call, or until two more blocks were issued. */
+ *    a copy-engine stream.  The input buffer of block b is then read asynchronously with respect to the chain's
+ *    stream, and issuing further blocks never waits for it on the host.  It may be changed or freed only after one of:
+ *    sdrb_chain_sync(); sdrb_chain_join() followed by a synchronise of the chain's stream; a lag-0 read of block b
+ *    (sdrb_chain_read_* right after issuing it); a lag-1 read issued after block b+1 (it waits for the back end of b,
+ *    which is ordered after everything that read b's input); or sdrb_chain_input_consumed(c, 0) returning 1. */
 int sdrb_chain_set_overlap(sdrb_chain* c, int on);
+
+/* 1 if the input buffer handed to the block issued `lag` (0 or 1) calls ago has been consumed completely (the H2D copy
+ * for process_host, the RF front end for process_device), 0 if it may still be read, < 0 on error (-sdrb_status).
+ * Never blocks. */
+int sdrb_chain_input_consumed(sdrb_chain* c, int lag);
 
 /* Makes the chain's stream wait (on the device, without blocking the host) for everything issued so far. */
 int sdrb_chain_join(sdrb_chain* c);
@@ -220,12 +228,21 @@ int sdrb_chain_stage(sdrb_chain* c, const char* name, float* h_out, int cap_per_
 size_t sdrb_chain_state_bytes(const sdrb_chain* c);
 int sdrb_chain_state_save(sdrb_chain* c, void* h_blob);
 int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob);
+/* Same with the size of the caller's buffer: a blob shorter than the size recorded in its header (a truncated file)
+ * is rejected with SDRB_ERR_INVALID instead of being read past its end.  After a load no results exist until the
+ * next block was processed (the read calls return SDRB_ERR_STATE). */
+int sdrb_chain_state_load_n(sdrb_chain* c, const void* h_blob, size_t blob_bytes);
 
 /* Mean device time per launch of each kernel family, in milliseconds, over the blocks processed since profiling was
  * switched on (CUDA event pairs recorded on the stream each kernel runs on; at most the last 128 blocks).
  * names/ms arrays of capacity cap; returns the count in *n. */
 int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int cap, int* n);
 int sdrb_chain_set_profiling(sdrb_chain* c, int on);
+/* Capacity events of the RDS back end since the chain was created: counts[0] blocks whose bit count exceeded
+ * sdrb_chain_info.max_bits, counts[1] blocks whose bits did not fit the frame-sync buffer, counts[2] blocks that completed
+ * more than max_groups groups.  All three are unreachable with the reference's rates (37 bits per block, 15 blocks per
+ * frame-sync call); a non-zero count means data was cut off and says where. */
+int sdrb_chain_rds_overflows(sdrb_chain* c, unsigned int counts[3]);
 /* Number of kernels launched by this chain so far. */
 long long sdrb_chain_launch_count(const sdrb_chain* c);
 

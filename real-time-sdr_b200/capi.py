@@ -27,6 +27,7 @@ EXPORTS = [
     "sdrb_chain_set_profiling", "sdrb_chain_launch_count", "sdrb_chain_set_overlap", "sdrb_pinned_alloc",
     "sdrb_pinned_free", "sdrb_chain_set_stream", "sdrb_chain_join", "sdrb_chain_read_results",
     "sdrb_manchester_decode", "sdrb_differential_decode", "sdrb_frame_sync",
+    "sdrb_chain_state_load_n", "sdrb_chain_input_consumed", "sdrb_chain_rds_overflows",
 ]
 
 
@@ -109,6 +110,9 @@ def load(path: str | None = None) -> C.CDLL:
     L.sdrb_chain_state_bytes.restype = sz
     L.sdrb_chain_state_save.argtypes = [vp, vp]
     L.sdrb_chain_state_load.argtypes = [vp, vp]
+    L.sdrb_chain_state_load_n.argtypes = [vp, vp, sz]
+    L.sdrb_chain_input_consumed.argtypes = [vp, ci]
+    L.sdrb_chain_rds_overflows.argtypes = [vp, C.POINTER(C.c_uint * 3)]
     L.sdrb_chain_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(cf), ci, C.POINTER(ci)]
     L.sdrb_chain_set_profiling.argtypes = [vp, ci]
     L.sdrb_chain_launch_count.argtypes = [vp]
@@ -260,7 +264,18 @@ class Chain:
         return buf.raw
 
     def state_load(self, blob: bytes):
-        check(self.L.sdrb_chain_state_load(self.h, blob))
+        check(self.L.sdrb_chain_state_load_n(self.h, blob, len(blob)))
+
+    def input_consumed(self, lag: int = 0) -> bool:
+        r = self.L.sdrb_chain_input_consumed(self.h, lag)
+        if r < 0:
+            raise SdrError(-r, self.L.sdrb_last_error().decode("utf-8", "replace"))
+        return bool(r)
+
+    def rds_overflows(self) -> tuple:
+        c = (C.c_uint * 3)()
+        check(self.L.sdrb_chain_rds_overflows(self.h, C.byref(c)))
+        return tuple(int(v) for v in c)
 
     def set_profiling(self, on: bool):
         check(self.L.sdrb_chain_set_profiling(self.h, 1 if on else 0))

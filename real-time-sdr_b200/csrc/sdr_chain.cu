@@ -75,6 +75,9 @@ struct sdrb_chain {
     int S = 0;
     int up = 1, down = 5;
     bool stereo = false, rds = false;
+    bool rds_gated = false;  // type 'r' in a mode without an RDS back end: records are reported as gated
+    int poisoned = 0;        // a launch failed in the middle of a block: the carried state is inconsistent (SDRB_ERR_STATE from then on)
+    long long blocks_since_load = 0;  // blocks processed since creation / the last state load: results exist only for those
     int pll_max_ctas = kPllMaxCtas;  // SMs given to k_pll (tuning knob: environment variable SDRB_PLL_MAX_CTAS)
     long long block = 0;  // index of the next block to process
     long long launches = 0;
@@ -82,7 +85,8 @@ struct sdrb_chain {
     bool own_stream = false;
     // overlap mode: front end of block b+1 concurrent with PLL / back end of block b (see process_block)
     cudaStream_t s_front = nullptr, s_pll = nullptr, s_back = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_front[kNRing] = {}, ev_pll[kNRing] = {}, ev_back[kNRing] = {}, ev_h2d[2] = {}, ev_join = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_front[kNRing] = {}, ev_pll[kNRing] = {}, ev_back[kNRing] = {}, ev_h2d[2] = {}, ev_consumed[2] = {}, ev_join = nullptr;
+    bool input_is_host = false;  // the block being issued comes from process_host (its input is consumed by the H2D copy)
     bool pending = false;  // work issued on the internal streams that the main stream has not been joined with
     // taps
     Taps101 rf_h, pilot_h, stereo_h, rds_h, rds114_h, rrc_h, audio_h;
@@ -100,6 +104,7 @@ struct sdrb_chain {
     float* d_filt_state[2] = {nullptr, nullptr};
     RdsStreamState* d_rds_state = nullptr;
     RdsRecord* d_rec[2] = {nullptr, nullptr};
+    unsigned int* d_rds_overflow = nullptr;  // [3], see RdsArgs::overflow
     // outputs, double buffered by block parity (a lagged read of block b-1 may overlap block b)
     int16_t* d_pcm[2] = {nullptr, nullptr};
     size_t pcm_pitch = 0;
@@ -191,6 +196,15 @@ int launch_audio_decim(sdrb_chain* c, const AudioArgs& a, cudaStream_t st) {
     return check_launch(c, "k_audio_decim", st);
 }
 
+// Host -> device copy of one block of every stream.  When the host rows are laid out with the device pitch (what a caller
+// gets by allocating its pinned ring with info.block_bytes rounded up to 256) the whole batch is ONE contiguous copy; a
+// pitched copy of n_streams rows otherwise.
+cudaError_t copy_rows_h2d(sdrb_chain* c, uint8_t* dst, const uint8_t* h_iq, size_t iq_pitch, cudaStream_t st) {
+    if (iq_pitch == c->iq_pitch)  // (the last row is only read up to its block bytes: the caller's buffer may end there)
+        return cudaMemcpyAsync(dst, h_iq, c->iq_pitch * (size_t)(c->S - 1) + (size_t)c->info.block_bytes, cudaMemcpyHostToDevice, st);
+    return cudaMemcpy2DAsync(dst, c->iq_pitch, h_iq, iq_pitch, c->info.block_bytes, c->S, cudaMemcpyHostToDevice, st);
+}
+
 // Makes the caller-visible stream wait for everything issued on the internal streams (no host blocking).
 int join_main(sdrb_chain* c) {
     if (!c->pending) return SDRB_OK;
@@ -207,7 +221,7 @@ int join_main(sdrb_chain* c) {
 //   pll(b)                                    waits: front(b)          (and pll(b-1): same stream)
 //   back(b)  = mixers + audio + RDS           waits: pll(b)            (and back(b-1): same stream)
 // so the FIR-heavy front end of block b+1 fills the machine while the latency-bound PLL of block b runs on a few SMs.
-int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent_t input_ready) {
+int process_block_impl(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent_t input_ready) {
     const long long b = c->block;
     const int S = c->S, n_if = c->info.if_block;
     const bool keep = c->cfg.keep_stages != 0;
@@ -248,6 +262,7 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
             default: return fail(SDRB_ERR_INVALID, "rf_decim must be 10, 4 or 3");
         }
         if (rc) return rc;
+        if (!c->input_is_host) CU(cudaEventRecord(c->ev_consumed[b & 1], sf));  // the caller's device buffer has been read
     }
     const int tiles = (n_if + kBankTile - 1) / kBankTile;
     const int bank_blocks = (int)(((long long)S * tiles + kBankWarps - 1) / kBankWarps);
@@ -372,6 +387,7 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
         a.rec = c->d_rec[b & 1];
         a.filt_out = keep ? c->d_rfilt : nullptr;
         a.clean_out = keep ? c->d_rclean : nullptr;
+        a.overflow = c->d_rds_overflow;
         const int rrc_tiles = (a.n_out + kRrcTile - 1) / kRrcTile;
         const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;
         const size_t smem = sizeof(float) * (round_up(n_if + kState, 4) + nfilt + nfilt / kRrcR + 8);
@@ -380,7 +396,18 @@ int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent
     }
     if (ov) CU(cudaEventRecord(c->ev_back[b % kNRing], sb));
     c->block = b + 1;
+    c->blocks_since_load++;
     return SDRB_OK;
+}
+
+// A failure after the first kernel of a block was enqueued leaves halos, rings and PLL state partly advanced while
+// c->block is not: such a chain cannot continue (or be retried) bit-exactly, so it is marked unusable.
+int process_block(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cudaEvent_t input_ready) {
+    if (c->poisoned) return fail(SDRB_ERR_STATE, "chain is unusable: a kernel launch failed in the middle of an earlier block");
+    const long long launches0 = c->launches;
+    const int rc = process_block_impl(c, d_iq, iq_pitch, input_ready);
+    if (rc != SDRB_OK && (c->launches != launches0 || rc == SDRB_ERR_CUDA)) c->poisoned = 1;
+    return rc;
 }
 
 }  // namespace
@@ -422,7 +449,7 @@ int sdrb_chain_destroy(sdrb_chain* c) {
     for (void* p : c->allocs) cudaFree(p);
     for (cudaStream_t st : {c->s_front, c->s_pll, c->s_back, c->s_h2d, c->s_d2h})
         if (st) cudaStreamDestroy(st);
-    for (cudaEvent_t e : {c->ev_in, c->ev_join, c->ev_h2d[0], c->ev_h2d[1]})
+    for (cudaEvent_t e : {c->ev_in, c->ev_join, c->ev_h2d[0], c->ev_h2d[1], c->ev_consumed[0], c->ev_consumed[1]})
         if (e) cudaEventDestroy(e);
     for (int i = 0; i < kNRing; i++)
         for (cudaEvent_t e : {c->ev_front[i], c->ev_pll[i], c->ev_back[i]})
@@ -445,8 +472,9 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
     if (cfg->type != 'm' && cfg->type != 's' && cfg->type != 'r') return fail(SDRB_ERR_INVALID, "bad type");
     if (cfg->rf_decim != 10 && cfg->rf_decim != 4 && cfg->rf_decim != 3) return fail(SDRB_ERR_INVALID, "rf_decim must be 10, 4 or 3");
     if (cfg->audio_upsample < 1 || cfg->audio_decim < 1) return fail(SDRB_ERR_INVALID, "bad audio resampling ratio");
-    if (cfg->type == 'r' && !(cfg->if_Fs == 240000 && cfg->audio_upsample == 1))
-        return fail(SDRB_ERR_INVALID, "RDS needs if_Fs = 240 kHz (mode 0): the reference hard-codes 247/640 and 39 samples per symbol");
+    if (cfg->rf_Fs <= 0 || cfg->if_Fs <= 0 || cfg->audio_Fc <= 0 || cfg->rf_Fc <= 0) return fail(SDRB_ERR_INVALID, "rates and cut-offs must be positive");
+    if ((long long)kTaps * cfg->audio_upsample > 65535) return fail(SDRB_ERR_INVALID, "101 * audio_upsample must fit an unsigned short (include/filter.h:19)");
+    if ((1470LL * cfg->audio_decim) / cfg->audio_upsample < kState + 12) return fail(SDRB_ERR_INVALID, "block too short for the 101-tap filters");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -474,14 +502,19 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
     c->up = cfg->audio_upsample;
     c->down = cfg->audio_decim;
     c->stereo = cfg->type != 'm';
-    c->rds = cfg->type == 'r';
+    // The RDS back end is built for the one configuration in which the reference's rds() decodes anything: 240 kHz IF and
+    // 39 samples per symbol (mode 0, src/project.cpp:67-74).  `project <1|2|3> r` still plays stereo audio while its rds
+    // thread runs the 57 kHz chain at rates it was not designed for and prints nothing (checked against the threaded
+    // reference binary in tests/); here such a chain is the stereo chain with every RDS record gated.
+    c->rds = cfg->type == 'r' && cfg->if_Fs == 240000 && cfg->audio_upsample == 1 && cfg->rf_Fs / cfg->rf_decim == 240000;
+    c->rds_gated = cfg->type == 'r' && !c->rds;
     sdrb_chain_info& I = c->info;
     I.block_pairs = (1470 * cfg->rf_decim * c->down) / c->up;  // src/rffrontend.cpp:21
     I.block_bytes = 2 * I.block_pairs;
     I.if_block = (1470 * c->down) / c->up;                     // src/mono.cpp:19
     I.audio_block = (int)(((long long)I.if_block * c->up) / c->down);
     I.pcm_per_block = I.audio_block * (c->stereo ? 2 : 1);
-    I.rds_block = (int)(((long long)I.if_block * kRdsUp) / kRdsDown);
+    I.rds_block = c->rds ? (int)(((long long)I.if_block * kRdsUp) / kRdsDown) : 0;
     I.max_bits = kRdsMaxBits;
     I.max_groups = kRdsMaxGroups;
     const int S = c->S, n_if = I.if_block;
@@ -515,29 +548,29 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
             TRYCU(cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio_lo));
         TRYCU(cudaStreamCreateWithPriority(&c->s_pll, cudaStreamNonBlocking, prio_hi));
     }
-    for (cudaEvent_t* e : {&c->ev_in, &c->ev_join, &c->ev_h2d[0], &c->ev_h2d[1]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&c->ev_in, &c->ev_join, &c->ev_h2d[0], &c->ev_h2d[1], &c->ev_consumed[0], &c->ev_consumed[1]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (int i = 0; i < kNRing; i++)
         for (cudaEvent_t* e : {&c->ev_front[i], &c->ev_pll[i], &c->ev_back[i]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 
     // ---- taps (all designed on the host, same libm as the reference build)
     std::vector<float> h(kTaps);
     const float if_fs_f = (float)(cfg->rf_Fs / cfg->rf_decim);
-    sdrb_design_lpf((float)cfg->rf_Fs, (float)cfg->rf_Fc, kTaps, h.data());            // src/rffrontend.cpp:24
+    TRY(sdrb_design_lpf((float)cfg->rf_Fs, (float)cfg->rf_Fc, kTaps, h.data()));            // src/rffrontend.cpp:24
     copy_taps(c->rf_h, h);
-    sdrb_design_bpf(if_fs_f, 18.5e3f, 19.5e3f, kTaps, h.data());                       // src/stereo.cpp:65
+    TRY(sdrb_design_bpf(if_fs_f, 18.5e3f, 19.5e3f, kTaps, h.data()));                       // src/stereo.cpp:65
     copy_taps(c->pilot_h, h);
-    sdrb_design_bpf(if_fs_f, 22e3f, 54e3f, kTaps, h.data());                           // src/stereo.cpp:67
+    TRY(sdrb_design_bpf(if_fs_f, 22e3f, 54e3f, kTaps, h.data()));                           // src/stereo.cpp:67
     copy_taps(c->stereo_h, h);
-    sdrb_design_bpf((float)cfg->if_Fs, 54e3f, 60e3f, kTaps, h.data());                 // src/rds.cpp:62
+    TRY(sdrb_design_bpf((float)cfg->if_Fs, 54e3f, 60e3f, kTaps, h.data()));                 // src/rds.cpp:62
     copy_taps(c->rds_h, h);
-    sdrb_design_bpf((float)cfg->if_Fs, 113.5e3f, 114.5e3f, kTaps, h.data());           // src/rds.cpp:63
+    TRY(sdrb_design_bpf((float)cfg->if_Fs, 113.5e3f, 114.5e3f, kTaps, h.data()));           // src/rds.cpp:63
     copy_taps(c->rds114_h, h);
-    sdrb_design_rrc((float)(2375 * 39), kTaps, h.data());                              // src/rds.cpp:65 (sps = 39)
+    TRY(sdrb_design_rrc((float)(2375 * 39), kTaps, h.data()));                              // src/rds.cpp:65 (sps = 39)
     copy_taps(c->rrc_h, h);
     {
         const int nh = kTaps * c->up;
         std::vector<float> ah(nh);
-        sdrb_design_lpf_gain((float)cfg->if_Fs * (float)c->up, (float)cfg->audio_Fc, nh, c->up, ah.data());  // src/mono.cpp:22
+        TRY(sdrb_design_lpf_gain((float)cfg->if_Fs * (float)c->up, (float)cfg->audio_Fc, nh, c->up, ah.data()));  // src/mono.cpp:22
         if (c->up == 1) {
             copy_taps(c->audio_h, ah);
         } else {
@@ -552,7 +585,7 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
     if (c->rds) {
         const int nh = kTaps * kRdsUp;
         std::vector<float> lh(nh);
-        sdrb_design_lpf_gain((float)(cfg->if_Fs * kRdsUp), 3e3f, nh, kRdsUp, lh.data());  // src/rds.cpp:61
+        TRY(sdrb_design_lpf_gain((float)(cfg->if_Fs * kRdsUp), 3e3f, nh, kRdsUp, lh.data()));  // src/rds.cpp:61
         // thread -> output residue: warp by warp, 32 residues whose input offsets floor(640 tp/247) differ modulo 32
         std::vector<int> thread_phase(256, -1);
         {
@@ -599,6 +632,7 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         for (int i = 0; i < 2; i++) TRY(dalloc(c, (void**)&c->d_filt_state[i], sizeof(float) * kState * S));
         TRY(dalloc(c, (void**)&c->d_rds_state, sizeof(RdsStreamState) * S));
         for (int i = 0; i < 2; i++) TRY(dalloc(c, (void**)&c->d_rec[i], sizeof(RdsRecord) * S));
+        TRY(dalloc(c, (void**)&c->d_rds_overflow, 3 * sizeof(unsigned int)));
     }
     {   // PLL initial state: feedbackI = 1, rest 0 (src/stereo.cpp:51-57, src/rds.cpp:51-56)
         std::vector<PllStateDev> init(S, PllStateDev{1.0f, 0.0f, 0.0f, 0.0f, 0.0});
@@ -660,6 +694,7 @@ int sdrb_chain_process_device(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitc
     if (iq_pitch < (size_t)c->info.block_bytes || (iq_pitch & 1)) return fail(SDRB_ERR_INVALID, "iq_pitch too small or odd");
     if ((reinterpret_cast<uintptr_t>(d_iq) & 1)) return fail(SDRB_ERR_INVALID, "d_iq must be 2-byte aligned");
     CU(cudaSetDevice(c->cfg.device));
+    c->input_is_host = false;
     return process_block(c, d_iq, iq_pitch, nullptr);
 }
 
@@ -669,18 +704,32 @@ int sdrb_chain_process_host(sdrb_chain* c, const uint8_t* h_iq, size_t iq_pitch)
     CU(cudaSetDevice(c->cfg.device));
     const long long b = c->block;
     uint8_t* dst = c->d_iq[b & 1];
+    if (c->poisoned) return fail(SDRB_ERR_STATE, "chain is unusable: a kernel launch failed in the middle of an earlier block");
+    c->input_is_host = true;
     if (!c->overlap) {
-        CU(cudaMemcpy2DAsync(dst, c->iq_pitch, h_iq, iq_pitch, c->info.block_bytes, c->S, cudaMemcpyHostToDevice, c->stream));
+        CU(copy_rows_h2d(c, dst, h_iq, iq_pitch, c->stream));
+        CU(cudaEventRecord(c->ev_consumed[b & 1], c->stream));
         return process_block(c, dst, c->iq_pitch, nullptr);
     }
     // copy engine stream: the staging buffer of parity b was last read by the front end of block b-2
     if (b >= 2) CU(cudaStreamWaitEvent(c->s_h2d, c->ev_front[(b - 2) % kNRing], 0));
     CU(cudaEventRecord(c->ev_in, c->stream));
     CU(cudaStreamWaitEvent(c->s_h2d, c->ev_in, 0));
-    CU(cudaMemcpy2DAsync(dst, c->iq_pitch, h_iq, iq_pitch, c->info.block_bytes, c->S, cudaMemcpyHostToDevice, c->s_h2d));
+    CU(copy_rows_h2d(c, dst, h_iq, iq_pitch, c->s_h2d));
     CU(cudaEventRecord(c->ev_h2d[b & 1], c->s_h2d));
+    CU(cudaEventRecord(c->ev_consumed[b & 1], c->s_h2d));
     c->pending = true;
     return process_block(c, dst, c->iq_pitch, c->ev_h2d[b & 1]);
+}
+
+int sdrb_chain_input_consumed(sdrb_chain* c, int lag) {
+    if (!c || lag < 0 || lag > 1) return -(int)fail(SDRB_ERR_INVALID, "bad argument");
+    if (c->blocks_since_load <= lag) return -(int)fail(SDRB_ERR_STATE, "that block has not been issued");
+    if (cudaSetDevice(c->cfg.device) != cudaSuccess) return -(int)SDRB_ERR_CUDA;
+    const cudaError_t e = cudaEventQuery(c->ev_consumed[(c->block - 1 - lag) & 1]);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) return 0;
+    return -cuda_fail(e, "cudaEventQuery");
 }
 
 int sdrb_chain_join(sdrb_chain* c) {
@@ -738,9 +787,15 @@ int sdrb_pinned_free(void* h_ptr) {
 int sdrb_chain_read_results(sdrb_chain* c, int lag, int16_t* h_pcm, size_t pcm_pitch, sdrb_rds_record* h_records) {
     if (!c) return fail(SDRB_ERR_INVALID, "null argument");
     if (lag < 0 || lag > 1) return fail(SDRB_ERR_INVALID, "lag must be 0 or 1");
-    if (c->block - lag <= 0) return fail(SDRB_ERR_STATE, "that block has not been processed yet");
+    if (c->poisoned) return fail(SDRB_ERR_STATE, "chain is unusable: a kernel launch failed in the middle of an earlier block");
+    if (c->block - lag <= 0 || c->blocks_since_load <= lag) return fail(SDRB_ERR_STATE, "that block has not been processed yet");
     if (h_pcm && pcm_pitch < (size_t)c->info.pcm_per_block) return fail(SDRB_ERR_INVALID, "pcm_pitch too small");
-    if (h_records && !c->rds) return fail(SDRB_ERR_STATE, "chain was created without RDS (type != 'r')");
+    if (h_records && !c->rds && !c->rds_gated) return fail(SDRB_ERR_STATE, "chain was created without RDS (type != 'r')");
+    if (h_records && c->rds_gated) {  // no RDS back end in this mode: every block reads as gated (cdr_offset = -1)
+        memset(h_records, 0, sizeof(sdrb_rds_record) * c->S);
+        for (int s = 0; s < c->S; s++) h_records[s].cdr_offset = -1;
+        h_records = nullptr;
+    }
     CU(cudaSetDevice(c->cfg.device));
     const long long b = c->block - 1 - lag;
     cudaStream_t st = c->stream;
@@ -813,8 +868,7 @@ int sdrb_rds_parse(uint64_t group, uint64_t* chars, uint64_t* output, char* text
 
 int sdrb_chain_stage(sdrb_chain* c, const char* name, float* h_out, int cap_per_stream, int* count) {
     if (!c || !name || !h_out || !count) return fail(SDRB_ERR_INVALID, "null argument");
-    if (!c->cfg.keep_stages) return fail(SDRB_ERR_STATE, "chain was created with keep_stages = 0");
-    if (c->block == 0) return fail(SDRB_ERR_STATE, "no block processed yet");
+    if (c->block == 0 || c->blocks_since_load == 0) return fail(SDRB_ERR_STATE, "no block processed yet");
     const long long b = c->block - 1;
     const int n_if = c->info.if_block;
     const float* src = nullptr;
@@ -822,7 +876,8 @@ int sdrb_chain_stage(sdrb_chain* c, const char* name, float* h_out, int cap_per_
     int n = 0;
     std::string s(name);
     auto ring = [&](const Ring& r) { src = r.base ? r.cur(b) : nullptr; pitch = r.pitch; n = r.n; };
-    auto flat = [&](const float* p, int cnt) { src = p; pitch = cnt; n = cnt; };
+    // ring-backed stages always exist; the flat ones are dumps that only a keep_stages chain writes
+    auto flat = [&](const float* p, int cnt) { src = c->cfg.keep_stages ? p : nullptr; pitch = cnt; n = cnt; };
     if (s == "fm_demod") ring(c->fm);
     else if (s == "pilot") ring(c->pilot);
     else if (s == "stereo_band") ring(c->sband);
@@ -840,7 +895,7 @@ int sdrb_chain_stage(sdrb_chain* c, const char* name, float* h_out, int cap_per_
     else if (s == "rds_filt") flat(c->d_rfilt, c->info.rds_block);
     else if (s == "rds_clean") flat(c->d_rclean, c->info.rds_block);
     else return fail(SDRB_ERR_INVALID, "unknown stage name: " + s);
-    if (!src) return fail(SDRB_ERR_STATE, "stage not produced in this configuration: " + s);
+    if (!src) return fail(SDRB_ERR_STATE, "stage not produced in this configuration (flat stages need keep_stages = 1): " + s);
     *count = n;
     if (cap_per_stream < n) return fail(SDRB_ERR_INVALID, "cap_per_stream too small");
     CU(cudaSetDevice(c->cfg.device));
@@ -878,8 +933,9 @@ std::vector<StateItem> state_items(sdrb_chain* c, long long b /* block that will
 struct StateHeader {
     uint32_t magic, n_streams, if_block, type;
     long long block;
+    unsigned long long total_bytes;  // of the whole blob, header included
 };
-constexpr uint32_t kStateMagic = 0x53445242u;
+constexpr uint32_t kStateMagic = 0x53445243u;
 }  // namespace
 
 size_t sdrb_chain_state_bytes(const sdrb_chain* c) {
@@ -894,7 +950,8 @@ int sdrb_chain_state_save(sdrb_chain* c, void* h_blob) {
     CU(cudaSetDevice(c->cfg.device));
     if (int rcj = join_main(c)) return rcj;
     CU(cudaStreamSynchronize(c->stream));
-    StateHeader hd{kStateMagic, (uint32_t)c->S, (uint32_t)c->info.if_block, (uint32_t)c->cfg.type, c->block};
+    if (c->poisoned) return fail(SDRB_ERR_STATE, "chain is unusable: a kernel launch failed in the middle of an earlier block");
+    StateHeader hd{kStateMagic, (uint32_t)c->S, (uint32_t)c->info.if_block, (uint32_t)c->cfg.type, c->block, sdrb_chain_state_bytes(c)};
     char* p = static_cast<char*>(h_blob);
     memcpy(p, &hd, sizeof hd);
     p += sizeof hd;
@@ -905,8 +962,11 @@ int sdrb_chain_state_save(sdrb_chain* c, void* h_blob) {
     return SDRB_OK;
 }
 
-int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob) {
+int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob) { return sdrb_chain_state_load_n(c, h_blob, (size_t)-1); }
+
+int sdrb_chain_state_load_n(sdrb_chain* c, const void* h_blob, size_t blob_bytes) {
     if (!c || !h_blob) return fail(SDRB_ERR_INVALID, "null argument");
+    if (blob_bytes < sizeof(StateHeader)) return fail(SDRB_ERR_INVALID, "state blob is shorter than its header");
     CU(cudaSetDevice(c->cfg.device));
     if (int rcj = join_main(c)) return rcj;
     CU(cudaStreamSynchronize(c->stream));
@@ -917,7 +977,17 @@ int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob) {
     if (hd.magic != kStateMagic || hd.n_streams != (uint32_t)c->S || hd.if_block != (uint32_t)c->info.if_block ||
         hd.type != (uint32_t)c->cfg.type)
         return fail(SDRB_ERR_INVALID, "state blob does not match this chain");
+    {   // the size the blob claims, the size this chain writes for that block index, and the size the caller holds must agree
+        const long long keep = c->block;
+        c->block = hd.block;
+        const size_t want = sdrb_chain_state_bytes(c);
+        c->block = keep;
+        if (hd.total_bytes != want || (blob_bytes != (size_t)-1 && blob_bytes < want))
+            return fail(SDRB_ERR_INVALID, "state blob is truncated or was written by a different configuration");
+    }
     c->block = hd.block;
+    c->blocks_since_load = 0;
+    c->poisoned = 0;  // a complete consistent state replaces whatever a failed block left behind
     for (auto& it : state_items(c, c->block)) {
         CU(cudaMemcpy2D(it.ptr, it.pitch_bytes, p, it.row_bytes, it.row_bytes, it.rows, cudaMemcpyHostToDevice));
         p += it.row_bytes * it.rows;
@@ -957,6 +1027,17 @@ int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int ca
 }
 
 long long sdrb_chain_launch_count(const sdrb_chain* c) { return c ? c->launches : 0; }
+
+int sdrb_chain_rds_overflows(sdrb_chain* c, unsigned int counts[3]) {
+    if (!c || !counts) return fail(SDRB_ERR_INVALID, "null argument");
+    counts[0] = counts[1] = counts[2] = 0;
+    if (!c->d_rds_overflow) return SDRB_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    if (int rcj = join_main(c)) return rcj;
+    CU(cudaMemcpyAsync(counts, c->d_rds_overflow, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SDRB_OK;
+}
 
 // ---- stand-alone batched primitives ---------------------------------------------------------------
 namespace {

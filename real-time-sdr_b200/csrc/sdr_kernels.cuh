@@ -926,6 +926,7 @@ struct RdsArgs {
     RdsRecord* rec;          // [n_streams]
     float* filt_out;         // optional [n_streams][n_out]
     float* clean_out;        // optional
+    unsigned int* overflow;  // [3] events in which a fixed capacity cut data off: bits per block, bit buffer, groups per block
 };
 
 // check_block's syndrome test (/root/reference/src/rds_utilities.cpp:357-366) on a 26-bit window held
@@ -1079,7 +1080,10 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     // ---- warp 0: Manchester pairing (src/rds_utilities.cpp:34-68) as two ballots, differential decode
     // (:70-88) as one shifted XOR on the 64-bit word.
     int nb = start_in + ((nsym - 1 - start_in) > 0 ? (nsym - 1 - start_in + 1) / 2 : 0);
-    if (nb > kRdsMaxBits) nb = kRdsMaxBits;
+    if (nb > kRdsMaxBits) {  // cannot happen with sps = 39 and 2836 samples per block (<= 37 bits); counted, never silent
+        nb = kRdsMaxBits;
+        if (t == 0) atomicAdd(a.overflow + 0, 1u);
+    }
     uint32_t wlo, whi;
     {
         int q = t, bit = 0;
@@ -1108,6 +1112,8 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
             st->bitbuf[w + 1] = (uint32_t)(lo >> 32);
             st->bitbuf[w + 2] = sh ? (uint32_t)(Dm >> (64 - sh)) : 0u;
             nbits += nb;
+        } else {
+            atomicAdd(a.overflow + 1, 1u);  // the block's bits are dropped (15 blocks x 37 bits + carry < kBitBufCap: unreachable)
         }
         rec->cdr_offset = off; rec->n_symbols = nsym; rec->n_bits = nb;
     }
@@ -1170,6 +1176,7 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     }
     if (t == 0) {
         rec->n_groups = ngroups < kRdsMaxGroups ? ngroups : kRdsMaxGroups;
+        if (ngroups > kRdsMaxGroups) atomicAdd(a.overflow + 2, 1u);  // 15 blocks hold at most 5.3 groups of 104 bits
         st->nbits = nbits;
         st->decoder_cont = decoder_cont;
         st->block_count = block_count + 1;

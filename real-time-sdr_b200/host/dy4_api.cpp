@@ -256,7 +256,31 @@ ReceiveChain::ReceiveChain(int mode, char type, int n_streams, int device) : n_(
     output_.assign(n_, 0);
     text_.assign(n_, std::string());
 }
+ReceiveChain::ReceiveChain(const ChainParams& p, char type, int n_streams, int device) : n_(n_streams), rds_(type != 'm' && p.rds_on) {
+    if (type != 'm' && type != 's' && type != 'r') throw std::invalid_argument("ReceiveChain: type must be 'm', 's' or 'r'");
+    sdrb_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.rf_Fs = p.rf_Fs; cfg.rf_Fc = p.rf_Fc; cfg.rf_taps = p.rf_taps; cfg.rf_decim = p.rf_decim;
+    cfg.audio_decim = p.audio_decim; cfg.audio_upsample = p.audio_upsample;
+    cfg.if_Fs = p.if_Fs; cfg.audio_Fc = p.audio_Fc; cfg.audio_Fs = p.audio_Fs; cfg.symbol_Fs = p.symbol_Fs;
+    cfg.rds_on = rds_ ? 1 : 0;
+    cfg.type = type == 'm' ? 'm' : (rds_ ? 'r' : 's');
+    cfg.n_streams = n_streams;
+    cfg.device = device;
+    ok(sdrb_chain_create(&cfg, &c_));
+    sdrb_chain_info inf;
+    ok(sdrb_chain_get_info(c_, &inf));
+    rds_ = rds_ && inf.rds_block > 0;  // modes without an RDS back end (see sdrb_chain_create) produce no records
+    chars_.assign(n_, 0);
+    output_.assign(n_, 0);
+    text_.assign(n_, std::string());
+}
 ReceiveChain::~ReceiveChain() { sdrb_chain_destroy(c_); }
+int ReceiveChain::if_block() const { sdrb_chain_info i; sdrb_chain_get_info(c_, &i); return i.if_block; }
+void ReceiveChain::read_fm_demod(float* out, size_t pitch_samples) {
+    int count = 0;
+    ok(sdrb_chain_stage(c_, "fm_demod", out, (int)pitch_samples, &count));
+}
 int ReceiveChain::block_bytes() const { sdrb_chain_info i; sdrb_chain_get_info(c_, &i); return i.block_bytes; }
 int ReceiveChain::pcm_per_block() const { sdrb_chain_info i; sdrb_chain_get_info(c_, &i); return i.pcm_per_block; }
 void ReceiveChain::process(const uint8_t* iq, size_t pitch) { ok(sdrb_chain_process_host(c_, iq, pitch)); }

@@ -12,8 +12,11 @@
 //     behaviour in the reference (e.g. x shorter than the carried state, src/filter.cpp:119,145) throw
 //     std::invalid_argument instead; GPU failures throw std::runtime_error with sdrb_last_error();
 //   * nothing here terminates the process.
-// The thread bodies RF_frontend/mono/stereo/rds are infinite loops around a queue in the reference; their batched
-// replacement is dy4::ReceiveChain below (one call per block for n_streams stations) and the sdr_project binary.
+// The thread bodies RF_frontend/mono/stereo/rds (infinite loops around a queue in the reference) are implemented in
+// dy4_threads.cpp on dy4::ReceiveChain below with their reference signatures (declared in compat/{rffrontend,mono,
+// stereo,rds}.h next to compat/{args,threadsafequeue}.h), so the reference's own src/project.cpp builds unchanged
+// against compat/ (host/project_dropin).  ReceiveChain itself is the batched form: one call per block for n_streams
+// stations; sdr_project is the single-process command line on top of it.
 #pragma once
 
 #include <cstdint>
@@ -63,15 +66,27 @@ namespace dy4 {
 
 // Batched replacement of the three thread bodies (src/rffrontend.cpp, mono.cpp|stereo.cpp, rds.cpp): mode and type
 // as on the reference's command line (src/project.cpp:67-132), n_streams independent stations on one GPU.
+// The numeric members of the reference's `struct args` (include/args.h:6-19), in its order.
+struct ChainParams {
+    int rf_Fs, rf_Fc, rf_taps, rf_decim;
+    int audio_decim, audio_upsample;
+    int if_Fs, audio_Fc, audio_Fs, symbol_Fs;
+    bool rds_on;
+};
+
 class ReceiveChain {
 public:
     ReceiveChain(int mode, char type, int n_streams = 1, int device = 0);
+    // From the parameter block the reference's main() fills (src/project.cpp:31-108); type 'm' = mono() is the audio
+    // body, 's' = stereo() (rds_on decides whether the RDS decoder prints, src/project.cpp:111-132).
+    ReceiveChain(const ChainParams& p, char type, int n_streams = 1, int device = 0);
     ~ReceiveChain();
     ReceiveChain(const ReceiveChain&) = delete;
     ReceiveChain& operator=(const ReceiveChain&) = delete;
 
     int block_bytes() const;      // bytes of interleaved uint8 IQ per station per block (src/rffrontend.cpp:21,48)
     int pcm_per_block() const;    // int16 samples per station per block (L,R interleaved for stereo)
+    int if_block() const;         // demodulated FM samples per station per block (what RF_frontend pushes, src/rffrontend.cpp:55)
     int n_streams() const { return n_; }
 
     // iq: n_streams rows of block_bytes() bytes, row pitch in bytes.  Results of this block are then available below.
@@ -80,6 +95,8 @@ public:
     void read_pcm(int16_t* pcm, size_t pitch_samples);
     // what rds() writes to stderr for this block, per station (src/rds_utilities.cpp:179-197); empty most of the time
     const std::vector<std::string>& rds_text();
+    // the block's demodulated FM signal, n_streams rows of if_block() floats (the payload of the reference's queue)
+    void read_fm_demod(float* out, size_t pitch_samples);
 
 private:
     sdrb_chain* c_ = nullptr;

@@ -137,8 +137,6 @@ def test_golden_fixture(capi):
 
 
 def test_errors_are_reported_not_fatal(capi):
-    with pytest.raises(capi.SdrError):
-        capi.Chain(2, "r", 1)          # RDS is only defined for the 240 kHz IF (mode 0)
     with capi.Chain(0, "m", 1) as ch:
         with pytest.raises(capi.SdrError):
             ch.read_pcm()              # nothing processed yet
@@ -186,8 +184,9 @@ def test_overlap_pipelined_lagged_reads(capi, oracle, station_iq):
 def test_full_size_batch_1024_streams(capi, oracle, station_iq):
     """BASELINE.json configs[4] at full width: 1024 stations (8 distinct ones, each delayed by s // 8 blocks like bench.py
     builds them) for 24 blocks in overlap mode with lagged reads.  Every one of the 1024 streams must equal the oracle run
-    of its own block sequence: PCM bit for bit and the same RDS bits."""
-    S, nblocks, M, NB = 1024, 24, 8, 8
+    of its own block sequence: PCM bit for bit, the same CDR offset in every block, the same RDS bits and the same group
+    registers from the two frame-sync calls the 40 blocks contain; no capacity counter may have moved."""
+    S, nblocks, M, NB = 1024, 40, 8, 8
     bb = 147000
     src = np.stack([station_iq(k, 0, NB).reshape(NB, bb) for k in range(M)])  # [station][block][bytes]
     sidx = np.arange(S)
@@ -208,20 +207,33 @@ def test_full_size_batch_1024_streams(capi, oracle, station_iq):
         all_pcm = np.zeros((nblocks, S, ch.info.pcm_per_block), np.int16)
         nbits = np.zeros((nblocks, S), np.int32)
         bits = np.zeros((nblocks, S, 48), np.uint8)
+        offs = np.zeros((nblocks, S), np.int32)
+        ngr = np.zeros((nblocks, S), np.int32)
+        grp = np.zeros((nblocks, S, 8), np.uint64)
+
+        def keep(b):
+            all_pcm[b], nbits[b], bits[b], offs[b], ngr[b], grp[b] = pcm, rec["n_bits"], rec["bits"], rec["cdr_offset"], rec["n_groups"], rec["groups"]
+
         bufs = [np.ascontiguousarray(step_input(g)) for g in range(min(nblocks, NB))]
         ch.process_host(bufs[0])
         for b in range(1, nblocks):
             ch.process_host(bufs[b % NB])
             ch.read_results(1, pcm, rec)
-            all_pcm[b - 1], nbits[b - 1], bits[b - 1] = pcm, rec["n_bits"], rec["bits"]
+            keep(b - 1)
         ch.read_results(0, pcm, rec)
-        all_pcm[nblocks - 1], nbits[nblocks - 1], bits[nblocks - 1] = pcm, rec["n_bits"], rec["bits"]
+        keep(nblocks - 1)
+        assert ch.rds_overflows() == (0, 0, 0)
     bad = []
     for s in range(S):
         w = want[(s % M, (s // M) % NB)]
         got_bits = np.concatenate([bits[b, s, : nbits[b, s]] for b in range(nblocks)]).astype(np.int32)
-        if not np.array_equal(all_pcm[:, s, :].reshape(-1), w["pcm"]) or not np.array_equal(got_bits, w["rds_bits"]):
+        got_groups = np.concatenate([grp[b, s, : ngr[b, s]] for b in range(nblocks)])
+        got_offs = offs[6:, s]  # the decoder is gated for the first six blocks (-1)
+        if (not np.array_equal(all_pcm[:, s, :].reshape(-1), w["pcm"]) or not np.array_equal(got_bits, w["rds_bits"])
+                or not np.array_equal(got_groups, w["groups"]) or not np.array_equal(got_offs, w["cdr_offset"][-got_offs.size:])
+                or not (offs[:6, s] == -1).all()):
             bad.append(s)
+    assert sum(len(w["groups"]) for w in want.values()) > 0, "the 40 blocks must complete RDS groups for this test to mean anything"
     assert not bad, f"{len(bad)} of {S} streams differ from their oracle run, first: {bad[:8]}"
 
 
@@ -326,3 +338,65 @@ def test_pll_cta_sizes(capi, oracle, station_iq, monkeypatch, cap, S):
     wants = {k: oracle.chain(0, "r", station_iq(k, 0, nblocks)) for k in range(3)}
     for s in range(S):
         _assert_same(got[s], wants[s % 3], ["pcm"] + RDS_KEYS, f"cap {cap} stream {s}")
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_type_r_outside_mode0_is_the_stereo_chain_with_gated_records(capi, oracle, station_iq, mode):
+    """`project <1|2|3> r` in the reference plays stereo audio and its RDS thread prints nothing
+    (tests/test_oracle_vs_ref.py::test_reference_rds_thread_is_silent_outside_mode0)."""
+    nblocks = 5
+    iq = station_iq(0, mode, nblocks)
+    want = oracle.chain(mode, "s", iq)
+    with capi.Chain(mode, "r", n_streams=2) as ch:
+        bb = ch.info.block_bytes
+        assert ch.info.rds_block == 0
+        pcm = []
+        for b in range(nblocks):
+            ch.process_host(np.stack([iq[b * bb:(b + 1) * bb]] * 2))
+            pcm.append(ch.read_pcm()[1].copy())
+            rec = ch.read_rds()
+            assert (rec["cdr_offset"] == -1).all() and (rec["n_bits"] == 0).all() and (rec["n_groups"] == 0).all()
+    assert np.array_equal(np.concatenate(pcm), want["pcm"])
+
+
+def test_state_blob_is_size_checked_and_results_need_a_block(capi, station_iq):
+    iq = station_iq(0, 0, 3)
+    with capi.Chain(0, "r", n_streams=2) as a:
+        bb = a.info.block_bytes
+        for b in range(2):
+            a.process_host(np.stack([iq[b * bb:(b + 1) * bb]] * 2))
+        blob = a.state_save()
+        assert a.rds_overflows() == (0, 0, 0)
+    with capi.Chain(0, "r", n_streams=2) as c2:
+        with pytest.raises(capi.SdrError) as e:
+            c2.state_load(blob[: len(blob) // 2])   # truncated file
+        assert e.value.code == capi.SDRB_ERR_INVALID
+        with pytest.raises(capi.SdrError):
+            c2.state_load(blob[:16])                 # shorter than the header
+        c2.state_load(blob)
+        with pytest.raises(capi.SdrError) as e:
+            c2.read_pcm()                            # loaded, but no block processed since: nothing to read
+        assert e.value.code == capi.SDRB_ERR_STATE
+        with pytest.raises(capi.SdrError):
+            c2.stage("fm_demod")
+        c2.process_host(np.stack([iq[2 * bb:3 * bb]] * 2))
+        c2.read_pcm()
+        assert c2.stage("fm_demod").shape == (2, c2.info.if_block)  # ring-backed stages need no keep_stages
+        with pytest.raises(capi.SdrError):
+            c2.stage("carrier")                      # flat dumps do
+    with capi.Chain(0, "s", n_streams=2) as c3:
+        with pytest.raises(capi.SdrError):
+            c3.state_load(blob)                      # a blob of another configuration
+
+
+def test_input_consumed_query(capi, station_iq):
+    iq = station_iq(0, 0, 4)
+    with capi.Chain(0, "s", n_streams=4) as ch:
+        ch.set_overlap(True)
+        bb = ch.info.block_bytes
+        with pytest.raises(capi.SdrError):
+            ch.input_consumed(0)
+        for b in range(3):
+            ch.process_host(np.stack([iq[b * bb:(b + 1) * bb]] * 4))
+        ch.sync()
+        assert ch.input_consumed(0) and ch.input_consumed(1)

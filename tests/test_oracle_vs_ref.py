@@ -2,6 +2,9 @@
 the container that has /root/reference; elsewhere the committed fixtures of test_oracle_golden.py apply)."""
 from __future__ import annotations
 
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
@@ -38,3 +41,45 @@ def test_edge_inputs(oracle, ref):
         a = oracle.chain(0, "r", iq, stages=("fm_demod", "carrier", "IPLL", "rds_clean"))
         b = ref.chain(0, "r", iq, stages=("fm_demod", "carrier", "IPLL", "rds_clean"))
         _cmp(a, b, ("fm_demod", "carrier", "IPLL", "rds_clean", "pcm", "cdr_offset", "rds_bits", "groups"))
+
+
+def _threaded(ref, mode, kind, iq):
+    """The reference's own three-thread binary (oracle/_ref/project) on a raw IQ byte string: (stdout, stderr)."""
+    if not os.path.exists(ref.project):
+        pytest.skip("oracle/_ref/project not built (no /root/reference here)")
+    r = subprocess.run([ref.project, str(mode), kind], input=iq.tobytes(), capture_output=True, timeout=300)
+    assert r.returncode == 1  # exit(1) at EOF, src/rffrontend.cpp:50-52
+    return r.stdout, r.stderr
+
+
+@pytest.mark.parametrize("mode,kind,nb", [(0, "r", 60), (0, "s", 8), (0, "m", 8), (2, "m", 6)])
+def test_threaded_reference_binary_end_to_end(oracle, ref, sdrgen, station_iq, mode, kind, nb):
+    """the unmodified threaded binary against the oracle, end to end.  Three padding blocks keep the
+    binary's EOF race (it exits while its consumers may still hold 1-2 blocks) away from the compared part."""
+    pad = 3
+    iq = station_iq(0, mode, nb + pad)
+    out, err = _threaded(ref, mode, kind, iq)
+    want = oracle.chain(mode, kind, iq)
+    pcm = want["pcm"].tobytes()
+    per_block = len(pcm) // (nb + pad)
+    assert len(out) >= nb * per_block and len(out) % 2 == 0
+    assert out == pcm[: len(out)]
+    if kind == "r":
+        text = bytes(want["text"])
+        assert err == text[: len(err)]
+        first = oracle.chain(mode, kind, iq[: nb * 2 * sdrgen.block_pairs(mode)])
+        assert len(err) >= len(bytes(first["text"])) > 0
+    else:
+        assert err == b""
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_reference_rds_thread_is_silent_outside_mode0(oracle, ref, station_iq, mode):
+    """`project <1|2|3> r`: stereo audio as in `s`, and an RDS thread that runs at rates it was not designed for and prints
+    nothing.  That is what lets libsdr_b200 serve type 'r' in those modes with the stereo chain and gated RDS records."""
+    nb, pad = 24, 3
+    iq = station_iq(0, mode, nb + pad)
+    out, err = _threaded(ref, mode, "r", iq)
+    assert err == b""
+    pcm = oracle.chain(mode, "s", iq)["pcm"].tobytes()
+    assert len(out) >= nb * (len(pcm) // (nb + pad)) and out == pcm[: len(out)]

@@ -79,3 +79,29 @@ def test_sdr_project_command_line(oracle, station_iq, tmp_path):
             assert r.stderr == bytes(want["text"])
     r = subprocess.run([exe, "9", "m"], input=b"", capture_output=True)
     assert r.returncode == 2
+
+
+@pytest.mark.parametrize("mode,kind,nb", [(0, "r", 60), (0, "s", 8), (0, "m", 8), (2, "m", 6), (1, "r", 6)])
+def test_reference_main_unchanged_on_the_b200_chain(oracle_mod, oracle, station_iq, mode, kind, nb):
+    """host/project_dropin = /root/reference/src/project.cpp compiled UNCHANGED against host/compat/ and linked with
+    libdy4_b200.so (RF_frontend / mono / stereo / rds(args*) on the GPU chain).  Its stdout and stderr against the
+    reference's own threaded binary (oracle/_ref/project) on the same input: the reference loses its last one or two blocks
+    to its EOF race (three padding blocks keep that away from the compared part), the drop-in writes every block, so the
+    reference's output must be a prefix of the drop-in's, and the drop-in's must equal the oracle's in full."""
+    exe = os.path.join(HOST, "project_dropin")
+    refexe = oracle_mod.RefHarness().project
+    assert os.path.exists(exe), "host/project_dropin missing: built by __graft_entry__.build() where /root/reference exists"
+    pad = 3
+    iq = station_iq(0, mode, nb + pad)
+    r = subprocess.run([exe, str(mode), kind], input=iq.tobytes(), capture_output=True, timeout=600)
+    assert r.returncode == 1, r.stderr[-500:]  # exit(1) at EOF like the reference (src/rffrontend.cpp:50-52)
+    want = oracle.chain(mode, "s" if (kind == "r" and mode != 0) else kind, iq)
+    assert r.stdout == want["pcm"].tobytes()
+    assert r.stderr == (bytes(want["text"]) if (kind == "r" and mode == 0) else b"")
+    if os.path.exists(refexe):
+        q = subprocess.run([refexe, str(mode), kind], input=iq.tobytes(), capture_output=True, timeout=600)
+        assert q.returncode == 1
+        per_block = len(r.stdout) // (nb + pad)
+        assert len(q.stdout) >= nb * per_block
+        assert r.stdout[: len(q.stdout)] == q.stdout
+        assert r.stderr[: len(q.stderr)] == q.stderr
