@@ -290,7 +290,7 @@ def _patch_pll_sample_count(capi, blob: bytes, S: int, n0: float) -> bytes:
     """Rewrites both PLL states inside a state blob (layout of sdrb_chain_state_save for a mode-0 'r' chain: header, IQ halo,
     ring halos fm 160 / rds_band 160 / trig19 4 / trig114 4 / stereo_dc 112 / rds_dc 112 floats, then the two PLL state arrays)."""
     import struct
-    off = 24 + S * 224 + S * 4 * (160 + 160 + 4 + 4 + 112 + 112)
+    off = 32 + S * 224 + S * 4 * (160 + 160 + 4 + 4 + 112 + 112)  # 32-byte header (magic, n_streams, if_block, type, block, total_bytes)
     out = bytearray(blob)
     for which, freq in ((0, 19e3), (1, 114e3)):
         for s in range(S):
