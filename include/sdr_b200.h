@@ -238,6 +238,13 @@ int sdrb_chain_state_load_n(sdrb_chain* c, const void* h_blob, size_t blob_bytes
  * names/ms arrays of capacity cap; returns the count in *n. */
 int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int cap, int* n);
 int sdrb_chain_set_profiling(sdrb_chain* c, int on);
+/* Health counter of the PLL kernel: how many times a station's 4-sample chunk left the speculative fast path and was
+ * recomputed by the careful path (counts[0] the 19 kHz loop, counts[1] the 114 kHz loop), since the chain was created.
+ * Results never depend on it; it is what explains a slow k_pll (normally ~1e-5 per sample). */
+int sdrb_chain_pll_redos(sdrb_chain* c, unsigned long long counts[2]);
+/* The same two totals followed by per-test counters (counts[2*(1+test)+loop]); the per-test part is only filled by a
+ * library built with -DSDRB_PLL_DIAG (tools/pll_drift.py --diag), zero otherwise. */
+int sdrb_chain_pll_redo_detail(sdrb_chain* c, unsigned long long counts[20]);
 /* Capacity events of the RDS back end since the chain was created: counts[0] blocks whose bit count exceeded
  * sdrb_chain_info.max_bits, counts[1] blocks whose bits did not fit the frame-sync buffer, counts[2] blocks that completed
  * more than max_groups groups.  All three are unreachable with the reference's rates (37 bits per block, 15 blocks per

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdr_b200.so")
+LIB_PATH = os.environ.get("SDRB_LIB") or os.path.join(_HERE, "libsdr_b200.so")  # SDRB_LIB: a variant build (tools/ only)
 
 SDRB_OK, SDRB_ERR_INVALID, SDRB_ERR_CUDA, SDRB_ERR_NO_DEVICE, SDRB_ERR_STATE = range(5)
 
@@ -28,6 +28,7 @@ EXPORTS = [
     "sdrb_pinned_free", "sdrb_chain_set_stream", "sdrb_chain_join", "sdrb_chain_read_results",
     "sdrb_manchester_decode", "sdrb_differential_decode", "sdrb_frame_sync",
     "sdrb_chain_state_load_n", "sdrb_chain_input_consumed", "sdrb_chain_rds_overflows",
+    "sdrb_chain_pll_redos", "sdrb_chain_pll_redo_detail",
 ]
 
 
@@ -112,6 +113,8 @@ def load(path: str | None = None) -> C.CDLL:
     L.sdrb_chain_state_load.argtypes = [vp, vp]
     L.sdrb_chain_state_load_n.argtypes = [vp, vp, sz]
     L.sdrb_chain_input_consumed.argtypes = [vp, ci]
+    L.sdrb_chain_pll_redo_detail.argtypes = [vp, C.POINTER(C.c_ulonglong * 20)]
+    L.sdrb_chain_pll_redos.argtypes = [vp, C.POINTER(C.c_ulonglong * 2)]
     L.sdrb_chain_rds_overflows.argtypes = [vp, C.POINTER(C.c_uint * 3)]
     L.sdrb_chain_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(cf), ci, C.POINTER(ci)]
     L.sdrb_chain_set_profiling.argtypes = [vp, ci]
@@ -271,6 +274,16 @@ class Chain:
         if r < 0:
             raise SdrError(-r, self.L.sdrb_last_error().decode("utf-8", "replace"))
         return bool(r)
+
+    def pll_redos(self) -> tuple:
+        c = (C.c_ulonglong * 2)()
+        check(self.L.sdrb_chain_pll_redos(self.h, C.byref(c)))
+        return tuple(int(v) for v in c)
+
+    def pll_redo_detail(self) -> list:
+        c = (C.c_ulonglong * 20)()
+        check(self.L.sdrb_chain_pll_redo_detail(self.h, C.byref(c)))
+        return [int(v) for v in c]
 
     def rds_overflows(self) -> tuple:
         c = (C.c_uint * 3)()

@@ -197,7 +197,15 @@ constexpr double kPTailLo = 0x1.9f31d0082efaap-169;
 constexpr double kP4Rest = 0x1.3198a2e037073p-69;  // pi/2 - P1 - P2 - P3 rounded to 53 bits
 constexpr double kPiH = 0x1.921fb54442d18p+1, kPiM = 0x1.1a62633145c07p-53, kPiL = -0x1.f1976b7ed8fbcp-109;
 constexpr double kPio2H = 0x1.921fb54442d18p+0, kPio2M = 0x1.1a62633145c07p-54, kPio2L = -0x1.f1976b7ed8fbcp-110;
-constexpr double kReduceLimit = 3.0e9;  // |x| below this: k < 2^31, exact Cody-Waite steps
+// |x| below this uses the reductions of this file.  2^45 rad is 1.8 years of the 114 kHz loop's NCO phase (2.98 rad per
+// sample at 240 kS/s); round 1 stopped at 3e9 (70 minutes), after which every step went through the library.
+constexpr double kReduceLimit = 0x1p45;
+// Smallest |r| for which the double-precision reductions below are trusted, given the quadrant count k: their absolute
+// error is ~|k| 2^-106 (the rounding of an intermediate of size |k| (pi/2 - PIO2H) and the part of pi/2 beyond 107 bits),
+// which has to stay below 2^-48 |r| for the acceptance tests to mean what they say.  Up to |k| = 2^28 that is the 2^-30 no
+// float comes closer than to a multiple of pi/2 (checked exhaustively below 3e9, tests/test_pllmath.py); beyond, arguments
+// this close go to the double-double tier (probability ~|k| 2^-58 per argument).
+SDRB_HD double reduce_rmin(double kd) { return fmax(0x1p-30, dmul(fabs(kd), 0x1p-58)); }
 
 // ---- sin / cos ----
 // fast tier: x - k*pi/2 with four fma steps.  Steps 1 and 2 are exact (x is a float, k*P1 and k*P2
@@ -276,7 +284,7 @@ SDRB_HD void sincos_fast(double x, double& s, double& c, bool& tiny) {
     r = dfma(-kd, kP2, r);
     r = dfma(-kd, kP3, r);
     r = dfma(-kd, kP4Rest, r);
-    tiny = (kd != 0.0) && fabs(r) < 0x1p-30;  // kd == 0: r = x exactly
+    tiny = (kd != 0.0) && fabs(r) < reduce_rmin(kd);  // kd == 0: r = x exactly
     double sr, cr_;
     sincos_poly(r, sr, cr_);
     sincos_quadrant((int)((long long)kd & 3), sr, cr_, s, c);
@@ -286,10 +294,10 @@ SDRB_HD void sincos_fast(double x, double& s, double& c, bool& tiny) {
 // in double-double.  Returns RN_double(sin x), RN_double(cos x) up to ~2^-100.
 SDRB_HD void sincos_slow(double x, double& s, double& c) {
     double kd = rint(dmul(x, kTwoOverPi));
-    double r2 = dfma(-kd, kP2, dfma(-kd, kP1, x));  // exact, see above
-    dd r = dd_add_d(dd{r2, 0.0}, -dmul(kd, kP3));   // products with the 22-bit pieces are exact
-    r = dd_add_d(r, -dmul(kd, kP4));
-    r = dd_add_d(r, -dmul(kd, kP5));
+    double r2 = dfma(-kd, kP2, dfma(-kd, kP1, x));  // exact: x - k P1 has at most log2|k| + 1 significant bits, then k P2 lines up
+    dd r = dd_add(dd{r2, 0.0}, dd_neg(two_prod(kd, kP3)));  // exact products (53 bits only hold them for |k| < 2^31)
+    r = dd_add(r, dd_neg(two_prod(kd, kP4)));
+    r = dd_add(r, dd_neg(two_prod(kd, kP5)));
     r = dd_add(r, dd_neg(two_prod(kd, kPTailHi)));
     r = dd_add_d(r, -dmul(kd, kPTailLo));
     dd z = dd_mul(r, r);
@@ -486,6 +494,7 @@ struct PllFast {
     int kq;
     bool generic_next;  // sa/cr/r/kq are not valid (fbI/fbQ are): use the general atan2 at the next step
     double magic;       // 1.5 * 2^(E+29), E = binade of the current NCO phase: td + magic - magic rounds td to float precision
+    uint32_t rmin_hi;   // high word of the smallest |r| the speculative step accepts in that binade (reduce_rmin, rounded up)
 };
 SDRB_HD uint32_t dhi(double v) {
 #if defined(__CUDA_ARCH__)
@@ -531,6 +540,11 @@ SDRB_HD float bitsf(uint32_t b) {
 }
 // 1.5 * 2^(E+29) for the binade E of v: adding it to a number of that binade leaves exactly 24 significant bits (RNE).
 SDRB_HD double float_round_magic(double v) { return mkd(((dhi(v) & 0x7FF00000u) + (29u << 20)) | (1u << 19), 0u); }
+// reduce_rmin for every argument of the binade of v, as the high word of a power of two: |k| < 2^(E+1) 2/pi, so 2^(E-57)
+SDRB_HD uint32_t reduce_rmin_hi(double v) {
+    const uint32_t t = (dhi(v) & 0x7FF00000u) - (57u << 20);
+    return ((dhi(v) & 0x7FF00000u) > (57u << 20) && t > 0x3E100000u) ? t : 0x3E100000u;
+}
 constexpr double kMagicRint = 6755399441055744.0;  // 1.5 * 2^52: x + magic - magic = rint(x), integer in the low word
 constexpr int kAtanTolLog2 = -43;                  // absolute error bound of the rotated phase detector, see above
 
@@ -580,7 +594,7 @@ SDRB_HD bool sincos_reduce2(double x, double& sa, double& cr_, double& r_out, in
     sincos_poly2(r, ra, sa, cr_);
     r_out = r;
     q_out = q;
-    return !(ra < 0x1p-30);
+    return !(ra < reduce_rmin(kd));
 }
 // (sin theta, cos theta) from the reduced pieces
 SDRB_HD void pll_cs(double sa, double cr_, double r, int kq, double& s0, double& c0) {
@@ -608,6 +622,7 @@ SDRB_HD float cos_lean_f(float t) {
 SDRB_HD void pll_fast_sincos(float trigArg, PllFast& f) {
     double x = (double)trigArg;
     f.magic = float_round_magic(x);
+    f.rmin_hi = reduce_rmin_hi(x);
     bool ok = fabs(x) < kReduceLimit && fabs(x) > 0x1p-100;
     if (ok) {
         double sa, cr_, r;
@@ -724,15 +739,26 @@ SDRB_HD unsigned ambig_abs(double v) {  // near_float_boundary_abs, branch-free
     return (unsigned)((E - (1023u - 17u)) > 18u) | (unsigned)(off <= 2u * thr);
 }
 
+// `bad` is a plain flag in product builds; with -DSDRB_PLL_DIAG (tools/pll_diag.sh) each test owns a bit so that the
+// careful-path counter can say which test sent a chunk there.
+#if defined(SDRB_PLL_DIAG)
+#define SDRB_BAD(cond, id) ((cond) ? (1u << (id)) : 0u)
+#else
+#define SDRB_BAD(cond, id) ((unsigned)(cond))
+#endif
 SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, const PllK& kk, unsigned& bad) {
     // -- beside the chain: needs only `in` and the previous step's reduction --
     // rin is the raw reciprocal approximation: `in` outside 2^-90 <= |in| < 2^90 (zero, subnormal, inf, NaN too) rejects
-    bad |= (unsigned)(((fbits(in) & 0x7FFFFFFFu) - 0x12800000u) >= (0x6C800000u - 0x12800000u));
+    bad |= SDRB_BAD(((fbits(in) & 0x7FFFFFFFu) - 0x12800000u) >= (0x6C800000u - 0x12800000u), 0);
     const uint32_t rhi = dhi(f.r);
     const uint32_t rs = rhi & 0x80000000u;  // r < 0
     const unsigned m = ((unsigned)f.kq + ((fbits(in) >> 31) << 1)) & 3u;
-    // -theta (+pi) = -r - m*pi/2 in (-pi, pi]:  mm = 0, -1, -+2 (by the sign of r), +1 for m = 0, 1, 2, 3
-    const uint32_t mmhi = (m & 1u) ? ((m & 2u) ? 0x3FF00000u : 0xBFF00000u) : ((m & 2u) ? (0xC0000000u ^ rs) : 0u);
+    // -theta (+pi) = -r - m*pi/2 in (-pi, pi]:  mm = 0, -1, +-2 (the sign of r: pi - r for r > 0, -pi - r for r < 0), +1
+    // for m = 0, 1, 2, 3.  (Round 1 carried the opposite sign for m = 2: |e| came out above pi, the wrap test below
+    // rejected it and the careful path produced the right value - bit-exact, but every sample whose input sign disagrees
+    // with the NCO's, a quarter of all samples once the loop is out of lock or the float phase grid is coarser than pi
+    // (45 s into a stream for the 114 kHz loop), cost a careful repeat and k_pll ran 6x slower from then on.)
+    const uint32_t mmhi = (m & 1u) ? ((m & 2u) ? 0x3FF00000u : 0xBFF00000u) : ((m & 2u) ? (0x40000000u ^ rs) : 0u);
     const double mm = mkd(mmhi, 0u);
     const double base = dfma(mm, kk.v[kKPio2M], dfma(mm, kk.v[kKPio2H], -f.r));
     const uint32_t bh = dhi(base);
@@ -758,7 +784,8 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     // (double)(float)td without the round trip: td + M - M with M = 1.5 * 2^(E+29) rounds td to 24 significant bits,
     // to nearest even, exactly like the conversion, provided td lies in the binade E that M was built for.  M comes from
     // the previous step's phase (the binade changes once per doubling of the phase); a mismatch counts as bad, and so
-    // the range tests of the phase (below kReduceLimit, not tiny) only have to be made where M is made.
+    // the range tests of the phase (below kReduceLimit, not tiny) only have to be made where M is made (and so is the
+    // smallest reduced argument that binade's quadrant counts allow, rmin_hi).
     const double xd = dadd(dadd(td, f.magic), -f.magic);
     // quarter-turn reduction and polynomials (sincos_reduce2, inlined so that its test joins `bad`).  The quadrant
     // count must come from xd, not td: once the phase passes 2^22 the float grid is coarser than pi/4, td and xd can
@@ -775,10 +802,10 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     // nibble d2f_known was told.  (The linearisation atan(u/v) = u/in needs |u/in| < 2^-22, which holds by construction:
     // |u/in| <= sa * cr * 4 * 2^-24 from the four float roundings, none of which can underflow for 2^-90 <= |in| < 2^90
     // and sa >= 2^-31, both enforced; a NaN/inf e cannot arise from an accepted `in` either.)
-    bad |= (unsigned)((dhi(e) & 0x7FFFFFFFu) >= 0x400921F9u) | ambig_abs(e) | (unsigned)(((bh & 0x7FFFFFFFu) - 0x3FFFFFFFu) <= 1u);
+    bad |= SDRB_BAD((dhi(e) & 0x7FFFFFFFu) >= 0x400921F9u, 1) | SDRB_BAD(ambig_abs(e), 2) | SDRB_BAD(((bh & 0x7FFFFFFFu) - 0x3FFFFFFFu) <= 1u, 3);
     // td left the binade of M; r tiny; sa / cr near a float rounding tie
-    bad |= (unsigned)((((dhi(td) & 0x7FF00000u) + (29u << 20)) | (1u << 19)) != dhi(f.magic)) | (unsigned)(rah < 0x3E100000u) |
-           ambig_rel_lo(sa) | ambig_rel_lo(cr_);
+    bad |= SDRB_BAD((((dhi(td) & 0x7FF00000u) + (29u << 20)) | (1u << 19)) != dhi(f.magic), 4) | SDRB_BAD(rah < f.rmin_hi, 5) |
+           SDRB_BAD(ambig_rel_lo(sa), 6) | SDRB_BAD(ambig_rel_lo(cr_), 7);
     f.sa = sa;
     f.cr = cr_;
     f.r = r;
@@ -802,15 +829,26 @@ SDRB_RARE void pll_redo4(float i0, float i1, float i2, float i3, double r0, doub
 
 // Four consecutive samples: speculative run, verified once; the careful path only on failure.
 // r0..r3 = raw reciprocal approximations 1/|in| of the samples (any value for an `in` the step rejects).
+// redo_ctr (device only, may be null): incremented once per lane and chunk that had to take the careful path.
 SDRB_HD void pll_chunk4(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, PllFast& f,
-                        const PllCoef& k, const PllK& kk, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3) {
+                        const PllCoef& k, const PllK& kk, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3,
+                        unsigned long long* redo_ctr = nullptr) {
     const PllFast saved = f;
-    unsigned bad = f.generic_next ? 1u : 0u;
+    unsigned bad = SDRB_BAD(f.generic_next, 8);
     t0 = pll_step_spec(i0, r0, f, k, kk, bad);
     t1 = pll_step_spec(i1, r1, f, k, kk, bad);
     t2 = pll_step_spec(i2, r2, f, k, kk, bad);
     t3 = pll_step_spec(i3, r3, f, k, kk, bad);
     if (bad) {  // only here does the state have to live in addressable memory (the out-of-line call)
+#if defined(__CUDA_ARCH__)
+        if (redo_ctr) atomicAdd(redo_ctr, 1ull);
+#if defined(SDRB_PLL_DIAG)
+        for (int b = 0; b < 9; b++)
+            if ((bad >> b) & 1u) atomicAdd(redo_ctr + 2 * (1 + b), 1ull);  // per-test counters behind the two totals
+#endif
+#else
+        (void)redo_ctr;
+#endif
         PllFast again = saved;
         float a0, a1, a2, a3;
         pll_redo4(i0, i1, i2, i3, r0, r1, r2, r3, again, k, tab, a0, a1, a2, a3);

@@ -105,6 +105,7 @@ struct sdrb_chain {
     RdsStreamState* d_rds_state = nullptr;
     RdsRecord* d_rec[2] = {nullptr, nullptr};
     unsigned int* d_rds_overflow = nullptr;  // [3], see RdsArgs::overflow
+    unsigned long long* d_pll_redo = nullptr;  // [2], see PllLoop::redo
     // outputs, double buffered by block parity (a lagged read of block b-1 may overlap block b)
     int16_t* d_pcm[2] = {nullptr, nullptr};
     size_t pcm_pitch = 0;
@@ -303,6 +304,8 @@ int process_block_impl(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cuda
         const float if_fs = (float)(c->cfg.rf_Fs / c->cfg.rf_decim);
         a.loop[0].x = c->pilot.cur(b); a.loop[0].x_pitch = c->pilot.pitch; a.loop[0].trig = c->trig19.view(b);
         a.loop[0].st = c->d_pll[0];
+        a.loop[0].redo = c->d_pll_redo;
+        a.loop[1].redo = c->d_pll_redo + 1;
         a.loop[0].coef = cr::pll_coef(19e3f, if_fs, 2.0f, 0.0f, 0.01f);        // src/stereo.cpp:77
         if (c->rds) {
             a.loop[1].x = c->gpilot.cur(b); a.loop[1].x_pitch = c->gpilot.pitch; a.loop[1].trig = c->trig114.view(b);
@@ -622,6 +625,7 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         TRY(ring_alloc(c, c->trig19, n_if, 4));
         TRY(ring_alloc(c, c->sdc, n_if, 112));
         TRY(dalloc(c, (void**)&c->d_pll[0], sizeof(PllStateDev) * S));
+        TRY(dalloc(c, (void**)&c->d_pll_redo, 20 * sizeof(unsigned long long)));  // [2] totals + 9 x [2] per-test counters of diagnostic builds
     }
     if (c->rds) {
         TRY(ring_alloc(c, c->rband, n_if, 160));
@@ -1027,6 +1031,29 @@ int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int ca
 }
 
 long long sdrb_chain_launch_count(const sdrb_chain* c) { return c ? c->launches : 0; }
+
+// diagnostic builds (-DSDRB_PLL_DIAG): counts[2 * (1 + test) + loop], see pllmath.cuh
+int sdrb_chain_pll_redo_detail(sdrb_chain* c, unsigned long long counts[20]) {
+    if (!c || !counts) return fail(SDRB_ERR_INVALID, "null argument");
+    memset(counts, 0, 20 * sizeof(unsigned long long));
+    if (!c->d_pll_redo) return SDRB_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    if (int rcj = join_main(c)) return rcj;
+    CU(cudaMemcpyAsync(counts, c->d_pll_redo, 20 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SDRB_OK;
+}
+
+int sdrb_chain_pll_redos(sdrb_chain* c, unsigned long long counts[2]) {
+    if (!c || !counts) return fail(SDRB_ERR_INVALID, "null argument");
+    counts[0] = counts[1] = 0;
+    if (!c->d_pll_redo) return SDRB_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    if (int rcj = join_main(c)) return rcj;
+    CU(cudaMemcpyAsync(counts, c->d_pll_redo, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SDRB_OK;
+}
 
 int sdrb_chain_rds_overflows(sdrb_chain* c, unsigned int counts[3]) {
     if (!c || !counts) return fail(SDRB_ERR_INVALID, "null argument");

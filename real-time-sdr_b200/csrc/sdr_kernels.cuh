@@ -555,6 +555,7 @@ struct PllLoop {
     RingView trig;   // trig.cur[i] = trigArg after input sample i
     PllStateDev* st; // [n_streams]
     cr::PllCoef coef;
+    unsigned long long* redo;  // health counter: lane-chunks (4 samples of one station) that took the careful path
 };
 
 struct PllArgs {
@@ -668,7 +669,7 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
             const float4 vn = *(j + 1 < kPllTileChunks ? cur + j + 1 : nxt);
             const double p0 = pll_recip(vn.x), p1 = pll_recip(vn.y), p2 = pll_recip(vn.z), p3 = pll_recip(vn.w);
             float4 o;
-            cr::pll_chunk4(vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, f, k, kk, tab, o.x, o.y, o.z, o.w);
+            cr::pll_chunk4(vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, f, k, kk, tab, o.x, o.y, o.z, o.w, lp.redo);
             o4[g] = o;
             vc = vn;
             q0 = p0; q1 = p1; q2 = p2; q3 = p3;

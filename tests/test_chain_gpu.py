@@ -303,11 +303,13 @@ def _patch_pll_sample_count(capi, blob: bytes, S: int, n0: float) -> bytes:
     return bytes(out)
 
 
-@pytest.mark.parametrize("n0", [3.0e6, 2.0e7, 4.0e8])
+@pytest.mark.parametrize("n0", [3.0e6, 2.0e7, 4.0e8, 1.3e9, 5.0e10])
 def test_chain_at_large_nco_phase(capi, oracle, station_iq, n0):
     """The batched PLL kernel hours into a run: both loops are placed at sample count n0 through the checkpoint interface
-    (the oracle through its test hook), where the float NCO phase has an ulp of up to 64 rad.  Everything downstream of the
-    PLLs (carrier, IPLL, audio, RDS samples) must still be bit-identical."""
+    (the oracle through its test hook), where the float NCO phase has an ulp of up to 16384 rad (n0 = 1.3e9 is 90 minutes in:
+    the 114 kHz loop's phase is beyond the 3e9 at which round 1's own reduction stopped; 5e10 is 58 hours).  Everything
+    downstream of the PLLs (carrier, IPLL, audio, RDS samples) must still be bit-identical, and the kernel must still be
+    on its fast path (the careful path produces the same values at several times the cost)."""
     nblocks, S = 10, 2
     iq = station_iq(0, 0, nblocks)
     stages = ["carrier", "IPLL", "stereo_filt", "rds_clean"]
@@ -322,9 +324,12 @@ def test_chain_at_large_nco_phase(capi, oracle, station_iq, n0):
             pcm.append(ch.read_pcm()[1].copy())
             for k in stages:
                 acc[k].append(ch.stage(k)[1])
+        redo = ch.pll_redos()
     got = {k: np.concatenate(v) for k, v in acc.items()}
     got["pcm"] = np.concatenate(pcm)
     _assert_same(got, want, ["pcm"] + stages, f"n0={n0}")
+    chunks = S * nblocks * (7350 // 4)
+    assert redo[0] < 0.01 * chunks and redo[1] < 0.01 * chunks, f"careful-path chunks {redo} of {chunks} per loop"
 
 
 @pytest.mark.parametrize("cap,S", [("1", 70), ("4", 200), ("2", 33)])

@@ -36,6 +36,25 @@ def test_sincos_scan_against_glibc(host):
     assert out[2] < out[5] * 1e-4, "the slow tier should be rare"
 
 
+def test_sincos_scan_above_3e9_against_glibc(host):
+    """2^31.5 .. 2^45 rad: what the NCO phase reaches between 70 minutes and 1.8 years of a stream.  Every 97th float; the
+    fast tier's quadrant count leaves 53-bit exactness there, the tiers' error bounds scale with it (reduce_rmin)."""
+    out = (C.c_uint64 * 6)()
+    host.crh_scan_sincos(0x4F32D05E, 0x56000000, 97, 8, out)  # 3e9 .. 2^45
+    assert out[5] > 1_000_000
+    assert out[0] == 0 and out[1] == 0, f"sin/cos mismatches vs glibc: {out[0]}/{out[1]}, first pattern {out[3]:#x}"
+    assert out[2] < out[5] * 2e-3, "the slow tier should stay rare"
+
+
+def test_sincos_dense_binades_above_3e9(host):
+    """Every float of two whole binades far out (2^36 = one day of the 114 kHz loop, and the last one before the limit)."""
+    for lo in (0x51800000, 0x55800000):  # [2^36, 2^37), [2^44, 2^45)
+        out = (C.c_uint64 * 6)()
+        host.crh_scan_sincos(lo, lo + 0x00800000, 1, 8, out)
+        assert out[5] == 1 << 23
+        assert out[0] == 0 and out[1] == 0, f"binade {lo:#x}: {out[0]}/{out[1]} mismatches, first {out[3]:#x}"
+
+
 def test_sincos_dense_in_nco_range(host):
     """Dense scan of the range the 19 kHz NCO phase lives in during the first seconds."""
     out = (C.c_uint64 * 6)()
@@ -44,7 +63,8 @@ def test_sincos_dense_in_nco_range(host):
 
 
 def test_sincos_special_values(host):
-    t = np.array([0.0, -0.0, 1e-30, -1e-30, 1.5707964, 3.1415927, 6.2831855, 1e-45, 2.5e9, -2.5e9, 4e9, np.inf, np.nan], np.float32)
+    t = np.array([0.0, -0.0, 1e-30, -1e-30, 1.5707964, 3.1415927, 6.2831855, 1e-45, 2.5e9, -2.5e9, 4e9, -7.4e9, 3.3e13, 3.6e13, 1e20, -3e38,
+                  np.inf, np.nan], np.float32)
     s, c = np.zeros_like(t), np.zeros_like(t)
     host.crh_sincos(t, t.size, s, c)
     with np.errstate(invalid="ignore"):
@@ -152,6 +172,7 @@ def test_lean_cosine_equals_glibc(host):
     rng = np.random.default_rng(21)
     t = np.concatenate([(rng.random(2_000_000) * 6e6).astype(np.float32), (rng.random(1_000_000) * 100).astype(np.float32),
                         -(rng.random(500_000) * 1e4).astype(np.float32), (rng.random(500_000) * 2.9e9).astype(np.float32),
+                        (rng.random(500_000) * 3.4e13).astype(np.float32), -(rng.random(200_000) * 1e11).astype(np.float32),
                         np.array([0.0, -0.0, 1e-30, 3.1415927, 1.5707964, 4e9, 1e20], np.float32)])
     c = np.zeros_like(t)
     host.crh_cos_lean(t, t.size, c)
@@ -159,7 +180,7 @@ def test_lean_cosine_equals_glibc(host):
 
 
 @pytest.mark.parametrize("freq,scale,bw", [(19e3, 2.0, 0.01), (114e3, 0.5, 0.001)])
-@pytest.mark.parametrize("n0", [2.0e6, 9.0e6, 4.0e7, 3.0e8])
+@pytest.mark.parametrize("n0", [2.0e6, 9.0e6, 4.0e7, 3.0e8, 1.3e9, 2.0e10, 3.0e12])
 def test_fast_recurrence_at_large_phase(host, oracle, oracle_mod, freq, scale, bw, n0):
     """Hours into a run the NCO phase is a float with an ulp of radians (2^22 rad is reached after 35 s / 6 s).  Start both
     recurrences from the same state far down the road: the float grid is then coarser than a quadrant, which is exactly
@@ -197,3 +218,8 @@ def test_fast_recurrence_at_large_phase(host, oracle, oracle_mod, freq, scale, b
     assert int((want.view(np.uint32) != got.view(np.uint32)).sum()) == 0
     assert [float(st.feedbackI), float(st.feedbackQ), float(st.integrator), float(st.phaseEst)] == [float(v) for v in st4]
     assert st.trigOffset == trig.value
+    # ... and it must stay on the fast path: out here the loop cannot follow its input any more (the phase grid is coarser
+    # than pi), every quadrant / input-sign combination occurs, and each one has to be handled by the speculative step.
+    # (Round 1 sent the "input sign opposite to the NCO's, quadrant 0 or 2" case to the careful path: right values, 6x the time.)
+    chunks = nb * (n // 4)
+    assert stats[0] < 0.005 * chunks, f"{stats[0]} of {chunks} chunks left the fast path"
