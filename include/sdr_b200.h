@@ -228,6 +228,10 @@ int sdrb_chain_stage(sdrb_chain* c, const char* name, float* h_out, int cap_per_
 size_t sdrb_chain_state_bytes(const sdrb_chain* c);
 int sdrb_chain_state_save(sdrb_chain* c, void* h_blob);
 int sdrb_chain_state_load(sdrb_chain* c, const void* h_blob);
+/* Byte offset, inside the blob sdrb_chain_state_save writes for the current block index, of a named item: "pll19" /
+ * "pll114" ([n_streams] x {float feedbackI, feedbackQ, integrator, phaseEst; double trigOffset}), "iq_halo",
+ * "rds_decoder", "rds_filt_state"; -1 if the chain has no such item.  For tools that edit a checkpoint. */
+long long sdrb_chain_state_item_offset(const sdrb_chain* c, const char* name);
 /* Same with the size of the caller's buffer: a blob shorter than the size recorded in its header (a truncated file)
  * is rejected with SDRB_ERR_INVALID instead of being read past its end.  After a load no results exist until the
  * next block was processed (the read calls return SDRB_ERR_STATE). */
@@ -238,6 +242,10 @@ int sdrb_chain_state_load_n(sdrb_chain* c, const void* h_blob, size_t blob_bytes
  * names/ms arrays of capacity cap; returns the count in *n. */
 int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int cap, int* n);
 int sdrb_chain_set_profiling(sdrb_chain* c, int on);
+/* Debugging aid (compute-sanitizer substitute): a chain created while the environment variable SDRB_GUARD=1 is set puts a
+ * 512-byte canary zone before and after every device allocation it makes.  This call verifies all of them: SDRB_OK and
+ * the number of allocations checked, or SDRB_ERR_STATE naming the allocation a kernel wrote outside of. */
+int sdrb_chain_check_guards(sdrb_chain* c, int* n_checked);
 /* Health counter of the PLL kernel: how many times a station's 4-sample chunk left the speculative fast path and was
  * recomputed by the careful path (counts[0] the 19 kHz loop, counts[1] the 114 kHz loop), since the chain was created.
  * Results never depend on it; it is what explains a slow k_pll (normally ~1e-5 per sample). */

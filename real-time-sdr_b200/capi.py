@@ -28,7 +28,8 @@ EXPORTS = [
     "sdrb_pinned_free", "sdrb_chain_set_stream", "sdrb_chain_join", "sdrb_chain_read_results",
     "sdrb_manchester_decode", "sdrb_differential_decode", "sdrb_frame_sync",
     "sdrb_chain_state_load_n", "sdrb_chain_input_consumed", "sdrb_chain_rds_overflows",
-    "sdrb_chain_pll_redos", "sdrb_chain_pll_redo_detail",
+    "sdrb_chain_pll_redos", "sdrb_chain_pll_redo_detail", "sdrb_chain_check_guards",
+    "sdrb_chain_state_item_offset",
 ]
 
 
@@ -113,6 +114,9 @@ def load(path: str | None = None) -> C.CDLL:
     L.sdrb_chain_state_load.argtypes = [vp, vp]
     L.sdrb_chain_state_load_n.argtypes = [vp, vp, sz]
     L.sdrb_chain_input_consumed.argtypes = [vp, ci]
+    L.sdrb_chain_state_item_offset.argtypes = [vp, C.c_char_p]
+    L.sdrb_chain_state_item_offset.restype = C.c_longlong
+    L.sdrb_chain_check_guards.argtypes = [vp, C.POINTER(ci)]
     L.sdrb_chain_pll_redo_detail.argtypes = [vp, C.POINTER(C.c_ulonglong * 20)]
     L.sdrb_chain_pll_redos.argtypes = [vp, C.POINTER(C.c_ulonglong * 2)]
     L.sdrb_chain_rds_overflows.argtypes = [vp, C.POINTER(C.c_uint * 3)]
@@ -266,6 +270,9 @@ class Chain:
         check(self.L.sdrb_chain_state_save(self.h, buf))
         return buf.raw
 
+    def state_item_offset(self, name: str) -> int:
+        return int(self.L.sdrb_chain_state_item_offset(self.h, name.encode()))
+
     def state_load(self, blob: bytes):
         check(self.L.sdrb_chain_state_load_n(self.h, blob, len(blob)))
 
@@ -279,6 +286,11 @@ class Chain:
         c = (C.c_ulonglong * 2)()
         check(self.L.sdrb_chain_pll_redos(self.h, C.byref(c)))
         return tuple(int(v) for v in c)
+
+    def check_guards(self) -> int:
+        n = C.c_int(0)
+        check(self.L.sdrb_chain_check_guards(self.h, C.byref(n)))
+        return n.value
 
     def pll_redo_detail(self) -> list:
         c = (C.c_ulonglong * 20)()

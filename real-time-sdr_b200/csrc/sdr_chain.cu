@@ -91,7 +91,7 @@ struct sdrb_chain {
     // taps
     Taps101 rf_h, pilot_h, stereo_h, rds_h, rds114_h, rrc_h, audio_h;
     float* d_audio_pm = nullptr;   // phase-major audio taps (up > 1)
-    float* d_rds_perm = nullptr;   // permuted RDS low-pass taps
+    float2* d_rds_pair = nullptr;  // RDS low-pass taps per thread, two per entry (see k_rds_backend)
     int* d_rds_thread_phase = nullptr;
     // input
     uint8_t* d_iq[2] = {nullptr, nullptr};  // staging for process_host
@@ -117,14 +117,33 @@ struct sdrb_chain {
     bool overlap = false;
     std::vector<Timed> timed;
     std::vector<void*> allocs;
+    bool guard = false;                                // SDRB_GUARD=1: canary zones around every allocation
+    struct GuardedAlloc { char* base; size_t bytes; };
+    std::vector<GuardedAlloc> guards;
 };
 
 namespace {
 
+// Guard mode (environment variable SDRB_GUARD=1 at chain creation; a debugging aid, compute-sanitizer being unavailable
+// on the GPU pool): every allocation gets a canary zone on both sides, sdrb_chain_check_guards() verifies them.
+constexpr size_t kGuardBytes = 512;
+constexpr int kGuardByte = 0xA5;
+
 int dalloc(sdrb_chain* c, void** p, size_t bytes, int fill = 0) {
-    CU(cudaMalloc(p, bytes));
-    c->allocs.push_back(*p);
-    CU(cudaMemsetAsync(*p, fill, bytes, c->stream));
+    if (!c->guard) {
+        CU(cudaMalloc(p, bytes));
+        c->allocs.push_back(*p);
+        CU(cudaMemsetAsync(*p, fill, bytes, c->stream));
+        return SDRB_OK;
+    }
+    const size_t body = round_up(bytes, 256);  // keeps the alignment cudaMalloc gives and the kernels rely on
+    char* base = nullptr;
+    CU(cudaMalloc((void**)&base, body + 2 * kGuardBytes));
+    c->allocs.push_back(base);
+    CU(cudaMemsetAsync(base, kGuardByte, body + 2 * kGuardBytes, c->stream));
+    CU(cudaMemsetAsync(base + kGuardBytes, fill, bytes, c->stream));
+    c->guards.push_back({base, bytes});
+    *p = base + kGuardBytes;
     return SDRB_OK;
 }
 
@@ -204,6 +223,12 @@ cudaError_t copy_rows_h2d(sdrb_chain* c, uint8_t* dst, const uint8_t* h_iq, size
     if (iq_pitch == c->iq_pitch)  // (the last row is only read up to its block bytes: the caller's buffer may end there)
         return cudaMemcpyAsync(dst, h_iq, c->iq_pitch * (size_t)(c->S - 1) + (size_t)c->info.block_bytes, cudaMemcpyHostToDevice, st);
     return cudaMemcpy2DAsync(dst, c->iq_pitch, h_iq, iq_pitch, c->info.block_bytes, c->S, cudaMemcpyHostToDevice, st);
+}
+
+size_t rds_backend_smem(int n_if, int n_out) {
+    const int rrc_tiles = (n_out + kRrcTile - 1) / kRrcTile;
+    const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;
+    return sizeof(float) * (2 * round_up((size_t)n_if + kState + 4, 2) + nfilt + nfilt / kRrcR + 8);
 }
 
 // Makes the caller-visible stream wait for everything issued on the internal streams (no host blocking).
@@ -381,7 +406,7 @@ int process_block_impl(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cuda
         RdsArgs a{};
         a.dc = c->rdc.cur(b); a.dc_pitch = c->rdc.pitch;
         a.n_in = n_if; a.n_out = c->info.rds_block; a.sps = 39; a.rds_on = c->cfg.rds_on;
-        a.taps_perm = c->d_rds_perm;
+        a.taps_pair = c->d_rds_pair;
         a.thread_phase = c->d_rds_thread_phase;
         a.rrc = c->rrc_h;
         a.filt_state_in = c->d_filt_state[b & 1];
@@ -391,9 +416,7 @@ int process_block_impl(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cuda
         a.filt_out = keep ? c->d_rfilt : nullptr;
         a.clean_out = keep ? c->d_rclean : nullptr;
         a.overflow = c->d_rds_overflow;
-        const int rrc_tiles = (a.n_out + kRrcTile - 1) / kRrcTile;
-        const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;
-        const size_t smem = sizeof(float) * (round_up(n_if + kState, 4) + nfilt + nfilt / kRrcR + 8);
+        const size_t smem = rds_backend_smem(n_if, a.n_out);
         k_rds_backend<<<S, kRdsThreads, smem, sb>>>(a);
         if ((rc = check_launch(c, "k_rds_backend", sb))) return rc;
     }
@@ -502,6 +525,7 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         const int v = atoi(e);
         if (v >= 1 && v <= 148) c->pll_max_ctas = v;
     }
+    if (const char* e = getenv("SDRB_GUARD")) c->guard = atoi(e) != 0;
     c->up = cfg->audio_upsample;
     c->down = cfg->audio_decim;
     c->stereo = cfg->type != 'm';
@@ -589,24 +613,40 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         const int nh = kTaps * kRdsUp;
         std::vector<float> lh(nh);
         TRY(sdrb_design_lpf_gain((float)(cfg->if_Fs * kRdsUp), 3e3f, nh, kRdsUp, lh.data()));  // src/rds.cpp:61
-        // thread -> output residue: warp by warp, 32 residues whose input offsets floor(640 tp/247) differ modulo 32
+        // thread -> output residue tp (outputs n = tp + 247 q).  A thread reads its input pairs with LDS.128 at pair index
+        // e0 - 2 i (+ 1280 per output pair), e0 = off0 + 2 - (off0 & 1), off0 = floor(640 tp / 247) + 100: a quarter-warp's
+        // eight 16-byte accesses are conflict free when (e0 / 2) mod 8 differs among its lanes, so residues are dealt to
+        // thread slots by that class (any left over take whatever slot is free).
         std::vector<int> thread_phase(256, -1);
         {
-            std::vector<std::vector<int>> by_bank(32);
-            for (int tp = 0; tp < kRdsUp; tp++) by_bank[((kRdsDown * tp) / kRdsUp) % 32].push_back(tp);
-            for (int b = 0; b < 32; b++)
-                for (size_t i = 0; i < by_bank[b].size(); i++) thread_phase[32 * i + b] = by_bank[b][i];  // at most 8 per bank
+            auto cls = [](int tp) { const int off0 = (kRdsDown * tp) / kRdsUp + kState; return ((off0 + 2 - (off0 & 1)) / 2) & 7; };
+            std::vector<int> left;
+            int next_slot[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+            for (int tp = 0; tp < kRdsUp; tp++) {
+                int& sl = next_slot[cls(tp)];
+                if (sl < 256) { thread_phase[sl] = tp; sl += 8; }
+                else left.push_back(tp);
+            }
+            for (int th = 0; th < 256 && !left.empty(); th++)
+                if (thread_phase[th] < 0) { thread_phase[th] = left.back(); left.pop_back(); }
         }
-        std::vector<float> perm((size_t)kTaps * 256, 0.0f);
+        std::vector<float2> pair((size_t)kResGroups * 256, make_float2(0.0f, 0.0f));
         for (int th = 0; th < 256; th++) {
             const int tp = thread_phase[th];
             if (tp < 0) continue;
             const int phase = (kRdsDown * tp) % kRdsUp;
-            for (int j = 0; j < kTaps; j++) perm[(size_t)j * 256 + th] = lh[phase + kRdsUp * j];
+            const int par = ((kRdsDown * tp) / kRdsUp + kState) & 1;
+            for (int i = 0; i < kResGroups; i++) {
+                const int jb = 2 * i + par, ja = jb - 1;  // taps of group i, MAC order ja then jb; out of range = zero tap
+                float2 h2 = make_float2(0.0f, 0.0f);
+                if (ja >= 0 && ja < kTaps) h2.x = lh[phase + kRdsUp * ja];
+                if (jb >= 0 && jb < kTaps) h2.y = lh[phase + kRdsUp * jb];
+                pair[(size_t)i * 256 + th] = h2;
+            }
         }
-        TRY(dalloc(c, (void**)&c->d_rds_perm, perm.size() * sizeof(float)));
+        TRY(dalloc(c, (void**)&c->d_rds_pair, pair.size() * sizeof(float2)));
         TRY(dalloc(c, (void**)&c->d_rds_thread_phase, 256 * sizeof(int)));
-        TRYCU(cudaMemcpyAsync(c->d_rds_perm, perm.data(), perm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        TRYCU(cudaMemcpyAsync(c->d_rds_pair, pair.data(), pair.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         TRYCU(cudaMemcpyAsync(c->d_rds_thread_phase, thread_phase.data(), 256 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         TRYCU(cudaStreamSynchronize(c->stream));
     }
@@ -675,10 +715,8 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         TRYCU(cudaFuncSetAttribute(k_pll<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPllSmemBytes));
     }
     if (c->rds) {
-        const int rrc_tiles = (I.rds_block + kRrcTile - 1) / kRrcTile;
-        const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;
-        const size_t smem = sizeof(float) * (round_up(n_if + kState, 4) + nfilt + nfilt / kRrcR + 8);
-        TRYCU(cudaFuncSetAttribute(k_rds_backend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (I.rds_block > kResQ * kRdsUp) { sdrb_chain_destroy(c); return fail(SDRB_ERR_INVALID, "RDS block too long for the resampler kernel"); }
+        TRYCU(cudaFuncSetAttribute(k_rds_backend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rds_backend_smem(n_if, I.rds_block)));
     }
     TRYCU(cudaStreamSynchronize(c->stream));
 #undef TRY
@@ -920,18 +958,19 @@ struct StateItem {
     size_t row_bytes; // bytes per stream row to save
     size_t pitch_bytes;
     int rows;
+    const char* name; // for sdrb_chain_state_item_offset
 };
 std::vector<StateItem> state_items(sdrb_chain* c, long long b /* block that will be processed next */) {
     std::vector<StateItem> v;
     const int S = c->S;
-    v.push_back({c->d_iq_halo[b & 1], (size_t)2 * kIqHaloPairs, (size_t)2 * kIqHaloPairs, S});
+    v.push_back({c->d_iq_halo[b & 1], (size_t)2 * kIqHaloPairs, (size_t)2 * kIqHaloPairs, S, "iq_halo"});
     for (Ring* r : {&c->fm, &c->pilot, &c->sband, &c->rband, &c->gpilot, &c->trig19, &c->trig114, &c->sdc, &c->rdc})
         if (r->base && r->halo > 0)
-            v.push_back({r->base + (size_t)(b % kNRing) * r->slot, (size_t)r->halo * sizeof(float), r->pitch * sizeof(float), S});
+            v.push_back({r->base + (size_t)(b % kNRing) * r->slot, (size_t)r->halo * sizeof(float), r->pitch * sizeof(float), S, "ring_halo"});
     for (int i = 0; i < 2; i++)
-        if (c->d_pll[i]) v.push_back({c->d_pll[i], sizeof(PllStateDev) * S, sizeof(PllStateDev) * S, 1});
-    if (c->d_filt_state[0]) v.push_back({c->d_filt_state[b & 1], sizeof(float) * kState * S, sizeof(float) * kState * S, 1});
-    if (c->d_rds_state) v.push_back({c->d_rds_state, sizeof(RdsStreamState) * S, sizeof(RdsStreamState) * S, 1});
+        if (c->d_pll[i]) v.push_back({c->d_pll[i], sizeof(PllStateDev) * S, sizeof(PllStateDev) * S, 1, i ? "pll114" : "pll19"});
+    if (c->d_filt_state[0]) v.push_back({c->d_filt_state[b & 1], sizeof(float) * kState * S, sizeof(float) * kState * S, 1, "rds_filt_state"});
+    if (c->d_rds_state) v.push_back({c->d_rds_state, sizeof(RdsStreamState) * S, sizeof(RdsStreamState) * S, 1, "rds_decoder"});
     return v;
 }
 struct StateHeader {
@@ -939,7 +978,7 @@ struct StateHeader {
     long long block;
     unsigned long long total_bytes;  // of the whole blob, header included
 };
-constexpr uint32_t kStateMagic = 0x53445243u;
+constexpr uint32_t kStateMagic = 0x53445244u;
 }  // namespace
 
 size_t sdrb_chain_state_bytes(const sdrb_chain* c) {
@@ -947,6 +986,16 @@ size_t sdrb_chain_state_bytes(const sdrb_chain* c) {
     size_t total = sizeof(StateHeader);
     for (auto& it : state_items(const_cast<sdrb_chain*>(c), c->block)) total += it.row_bytes * it.rows;
     return total;
+}
+
+long long sdrb_chain_state_item_offset(const sdrb_chain* c, const char* name) {
+    if (!c || !name) return -1;
+    size_t off = sizeof(StateHeader);
+    for (auto& it : state_items(const_cast<sdrb_chain*>(c), c->block)) {
+        if (strcmp(it.name, name) == 0) return (long long)off;
+        off += it.row_bytes * it.rows;
+    }
+    return -1;
 }
 
 int sdrb_chain_state_save(sdrb_chain* c, void* h_blob) {
@@ -1033,6 +1082,30 @@ int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int ca
 long long sdrb_chain_launch_count(const sdrb_chain* c) { return c ? c->launches : 0; }
 
 // diagnostic builds (-DSDRB_PLL_DIAG): counts[2 * (1 + test) + loop], see pllmath.cuh
+int sdrb_chain_check_guards(sdrb_chain* c, int* n_checked) {
+    if (!c) return fail(SDRB_ERR_INVALID, "null argument");
+    if (n_checked) *n_checked = 0;
+    if (!c->guard) return fail(SDRB_ERR_STATE, "chain was created without SDRB_GUARD=1");
+    CU(cudaSetDevice(c->cfg.device));
+    if (int rcj = join_main(c)) return rcj;
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<unsigned char> lo(kGuardBytes), hi(kGuardBytes + 256);
+    int idx = 0;
+    for (auto& g : c->guards) {
+        const size_t body = round_up(g.bytes, 256);
+        const size_t tail = kGuardBytes + (body - g.bytes);  // the alignment slack behind the buffer is canary too
+        CU(cudaMemcpy(lo.data(), g.base, kGuardBytes, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hi.data(), g.base + kGuardBytes + g.bytes, tail, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < kGuardBytes; i++)
+            if (lo[i] != kGuardByte) return fail(SDRB_ERR_STATE, "guard zone BEFORE allocation #" + std::to_string(idx) + " (" + std::to_string(g.bytes) + " bytes) was overwritten");
+        for (size_t i = 0; i < tail; i++)
+            if (hi[i] != kGuardByte) return fail(SDRB_ERR_STATE, "guard zone AFTER allocation #" + std::to_string(idx) + " (" + std::to_string(g.bytes) + " bytes) was overwritten at +" + std::to_string(i));
+        idx++;
+    }
+    if (n_checked) *n_checked = idx;
+    return SDRB_OK;
+}
+
 int sdrb_chain_pll_redo_detail(sdrb_chain* c, unsigned long long counts[20]) {
     if (!c || !counts) return fail(SDRB_ERR_INVALID, "null argument");
     memset(counts, 0, 20 * sizeof(unsigned long long));

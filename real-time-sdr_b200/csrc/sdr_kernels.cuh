@@ -918,7 +918,7 @@ struct RdsArgs {
     int n_out;             // n_in*247/640
     int sps;
     int rds_on;
-    const float* taps_perm;  // [kTaps][256]: taps_perm[j*256 + thread] = h_lpf[(640*tp % 247) + 247*j], tp = thread_phase[thread]
+    const float2* taps_pair; // [kResGroups][256]: the thread's polyphase branch h_lpf[phase + 247 j], two taps per entry, see k_rds_backend
     const int* thread_phase; // [256]: the output residue tp (n = tp mod 247) each thread owns, -1 = idle
     Taps101 rrc;
     float* filt_state_in;    // [n_streams][kState] last rds_filt samples of the previous block
@@ -956,17 +956,18 @@ __device__ __forceinline__ uint32_t bitbuf_window26(const uint32_t* buf, int idx
 
 constexpr int kRrcR = 12;
 constexpr int kRrcTile = kRrcR * kRdsThreads;  // 3072 outputs per pass
-constexpr int kResQ = 12;                      // resampler outputs per thread per pass
+constexpr int kResQ = 12;                      // resampler outputs per thread: ceil(2836 / 247); the kernel requires n_out <= 12 * 247
+constexpr int kResGroups = 51;                 // tap groups (two taps each) per polyphase branch
 
 __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_constant__ RdsArgs a) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int s = blockIdx.x;
     const int t = threadIdx.x;
     const int n_in = a.n_in, n_out = a.n_out;
     const int rrc_tiles = (n_out + kRrcTile - 1) / kRrcTile;
     const int nfilt_pad = rrc_tiles * kRrcTile + kState;
-    float* sdc = smem;                                // [n_in + kState]; later reused as sclean [n_out]
-    float* sfilt = smem + (n_in + kState + 3) / 4 * 4;  // padded layout, pad_pos<kRrcR>
+    float2* sP = reinterpret_cast<float2*>(smem);        // [n_in + kState + 4] input pairs; later reused as sclean [n_out]
+    float* sfilt = smem + 2 * ((n_in + kState + 4 + 1) / 2 * 2);  // padded layout, pad_pos<kRrcR>
     __shared__ int ssum[64];
     __shared__ int ssym[160];
     __shared__ int8_t stype[kBitBufWords * 32];
@@ -980,9 +981,21 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     const int start_in = st->start, half_in = st->half_symbol, last_in = st->last_bit;
     const int nbits_in = st->nbits, decoder_cont_in = st->decoder_cont;
 
-    // ---- stage rds_dc (with the carried 100-sample state in front)
-    const float* dc = a.dc + (size_t)s * a.dc_pitch - kState;
-    for (int u = t; u < n_in + kState; u += kRdsThreads) sdc[u] = dc[u];
+    // ---- stage rds_dc (with the carried 100-sample state in front) as PAIRS: sP[u + 2] = (x[u], x[u + 640]).
+    // Outputs n and n + 247 of the resampler read inputs 640 apart, so one 64-bit word feeds both lanes of a packed MAC and
+    // one LDS.128 (two consecutive u) feeds two taps of two outputs.  Two zero entries in front and behind: the zero taps
+    // that pad a thread's branch to whole groups (below) multiply them.
+    const int nx = n_in + kState;
+    {
+        const float* dc = a.dc + (size_t)s * a.dc_pitch - kState;
+        for (int u = t; u < nx; u += kRdsThreads) {
+            const float x = dc[u];
+            sP[u + 2].x = x;
+            if (u >= kRdsDown) sP[u - kRdsDown + 2].y = x;
+        }
+    }
+    for (int u = nx - kRdsDown + t; u < nx + 2; u += kRdsThreads) sP[u + 2].y = 0.0f;  // partners beyond the block
+    if (t < 2) { sP[t] = make_float2(0.0f, 0.0f); sP[nx + 2 + t].x = 0.0f; }
     for (int u = t; u < kState; u += kRdsThreads)
         sfilt[pad_pos<kRrcR>(u)] = a.filt_state_in[(size_t)s * kState + u];
     for (int u = n_out + kState + t; u < nfilt_pad; u += kRdsThreads) sfilt[pad_pos<kRrcR>(u)] = 0.0f;
@@ -990,43 +1003,45 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     __syncthreads();
 
     // ---- 247/640 resampler (/root/reference/src/filter.cpp:123-147, src/rds.cpp:130).
-    // Outputs n and n+247 share the polyphase branch, so one thread owns n = tp + 247 q and keeps its 101 branch taps
-    // h[phase + 247 j] in flight once per pass over q.  Which tp a thread owns is a host-made permutation
-    // (thread_phase): the 32 lanes of a warp get input offsets floor(640 tp / 247) that are distinct modulo 32, so the
-    // one shared-memory load per MAC of this stage is bank-conflict free (in natural order it is 2.6-way conflicted).
+    // Outputs n and n+247 share the polyphase branch, so one thread owns n = tp + 247 q, q = 0..11, and streams its 101
+    // branch taps h[phase + 247 j] once; outputs 2p and 2p+1 form one packed accumulator (their inputs are the two halves of
+    // a pair, see above).  Taps come two at a time (j_a, j_b = j_a + 1, MAC order j_a then j_b = the reference's ascending
+    // k), with j_b of the same parity as the thread's input offset so that the pair address off - j_b is 16-byte aligned for
+    // LDS.128; the branch is zero-padded to 51 such groups by the host (a zero tap adds +-0 to the accumulator: no effect).
+    // Which tp a thread owns is a host-made permutation (thread_phase) that spreads each quarter-warp's 16-byte accesses over
+    // all eight 16-byte bank groups.
     const int tp = a.thread_phase[t];
     if (tp >= 0) {
-        const int base = (kRdsDown * tp) / kRdsUp;  // (n*down - phase)/up for q = 0
-        for (int q0 = 0; q0 * kRdsUp + tp < n_out; q0 += kResQ) {
-            float acc[kResQ];
-            int off[kResQ];
+        const int off0 = (kRdsDown * tp) / kRdsUp + kState;  // index of x[(n*down - phase)/up] for q = 0
+        const float2* pbase = sP + 2 + off0 - ((off0 & 1) ? 1 : 0);  // &pair(off0 - j_b) for group 0 (j_b = 0 or 1)
+        float2 acc[kResQ / 2];
 #pragma unroll
-            for (int qq = 0; qq < kResQ; qq++) {
-                acc[qq] = 0.0f;
-                int n = (q0 + qq) * kRdsUp + tp;
-                off[qq] = (n < n_out) ? kRdsDown * (q0 + qq) + base + kState : kState;
+        for (int pq = 0; pq < kResQ / 2; pq++) acc[pq] = make_float2(0.0f, 0.0f);
+#pragma unroll 3
+        for (int i = 0; i < kResGroups; i++) {
+            const float2 h = __ldg(a.taps_pair + i * 256 + t);
+#pragma unroll
+            for (int pq = 0; pq < kResQ / 2; pq++) {
+                const float4 v = *reinterpret_cast<const float4*>(pbase + 2 * kRdsDown * pq - 2 * i);  // pair(u), pair(u+1)
+                acc[pq] = mac(acc[pq], h.x, make_float2(v.z, v.w));  // tap j_a on x[off - j_a] = pair(u + 1)
+                acc[pq] = mac(acc[pq], h.y, make_float2(v.x, v.y));  // tap j_b on x[off - j_b] = pair(u)
             }
-#pragma unroll 8  // eight tap loads in flight ahead of their MACs: 0.117 -> 0.086 ms for the kernel (4: 0.111, 16: 0.086)
-            for (int j = 0; j < kTaps; j++) {
-                const float hj = __ldg(a.taps_perm + j * 256 + t);
+        }
 #pragma unroll
-                for (int qq = 0; qq < kResQ; qq++) acc[qq] = mac(acc[qq], hj, sdc[off[qq] - j]);
-            }
-#pragma unroll
-            for (int qq = 0; qq < kResQ; qq++) {
-                int n = (q0 + qq) * kRdsUp + tp;
-                if (n < n_out) {
-                    sfilt[pad_pos<kRrcR>(n + kState)] = acc[qq];
-                    if (a.filt_out) a.filt_out[(size_t)s * n_out + n] = acc[qq];
-                    if (n >= n_out - kState) a.filt_state_out[(size_t)s * kState + (n - (n_out - kState))] = acc[qq];
-                }
+        for (int qq = 0; qq < kResQ; qq++) {
+            const int n = qq * kRdsUp + tp;
+            const float y = (qq & 1) ? acc[qq / 2].y : acc[qq / 2].x;
+            if (n < n_out) {
+                sfilt[pad_pos<kRrcR>(n + kState)] = y;
+                if (a.filt_out) a.filt_out[(size_t)s * n_out + n] = y;
+                if (n >= n_out - kState) a.filt_state_out[(size_t)s * kState + (n - (n_out - kState))] = y;
             }
         }
     }
     __syncthreads();
 
     // ---- RRC matched filter (src/rds.cpp:133), 12 consecutive outputs per thread
-    float* sclean = sdc;
+    float* sclean = smem;
     for (int tile = 0; tile < rrc_tiles; tile++) {
         float acc[kRrcR];
 #pragma unroll

@@ -286,17 +286,17 @@ def test_argument_checks(capi):
         assert ch.read_pcm().shape == (2, 1470)
 
 
-def _patch_pll_sample_count(capi, blob: bytes, S: int, n0: float) -> bytes:
-    """Rewrites both PLL states inside a state blob (layout of sdrb_chain_state_save for a mode-0 'r' chain: header, IQ halo,
-    ring halos fm 160 / rds_band 160 / trig19 4 / trig114 4 / stereo_dc 112 / rds_dc 112 floats, then the two PLL state arrays)."""
+def _patch_pll_sample_count(ch, blob: bytes, S: int, n0: float) -> bytes:
+    """Rewrites both PLL states inside a state blob (their offsets come from sdrb_chain_state_item_offset)."""
     import struct
-    off = 32 + S * 224 + S * 4 * (160 + 160 + 4 + 4 + 112 + 112)  # 32-byte header (magic, n_streams, if_block, type, block, total_bytes)
+    offs = (ch.state_item_offset("pll19"), ch.state_item_offset("pll114"))
+    assert min(offs) > 0
     out = bytearray(blob)
     for which, freq in ((0, 19e3), (1, 114e3)):
         for s in range(S):
-            o = off + (which * S + s) * 24
+            o = offs[which] + s * 24
             fbI, fbQ, integ, phase, trig = struct.unpack_from("<4fd", out, o)
-            assert (fbI, fbQ, integ, phase, trig) == (1.0, 0.0, 0.0, 0.0, 0.0), "blob layout changed: fresh PLL state expected here"
+            assert (fbI, fbQ, integ, phase, trig) == (1.0, 0.0, 0.0, 0.0, 0.0), "fresh PLL state expected here"
             th = np.float32(2 * np.pi * float(np.float32(freq) / np.float32(240000.0)) * n0 + phase)
             struct.pack_into("<4fd", out, o, float(np.float32(np.cos(np.float64(th)))), float(np.float32(np.sin(np.float64(th)))),
                              integ, phase, float(n0))
@@ -317,7 +317,7 @@ def test_chain_at_large_nco_phase(capi, oracle, station_iq, n0):
     acc = {k: [] for k in stages}
     pcm = []
     with capi.Chain(0, "r", n_streams=S, keep_stages=True) as ch:
-        ch.state_load(_patch_pll_sample_count(capi, ch.state_save(), S, n0))
+        ch.state_load(_patch_pll_sample_count(ch, ch.state_save(), S, n0))
         bb = ch.info.block_bytes
         for b in range(nblocks):
             ch.process_host(np.stack([iq[b * bb:(b + 1) * bb]] * S))
@@ -405,3 +405,27 @@ def test_input_consumed_query(capi, station_iq):
             ch.process_host(np.stack([iq[b * bb:(b + 1) * bb]] * 4))
         ch.sync()
         assert ch.input_consumed(0) and ch.input_consumed(1)
+
+
+@pytest.mark.parametrize("mode,kind,S,nblocks,overlap", [(0, "r", 33, 8, True), (2, "m", 3, 3, False), (3, "s", 3, 3, False), (1, "s", 5, 3, True),
+                                                        (0, "r", 1, 22, False)])
+def test_guard_zones_stay_intact(capi, oracle, station_iq, monkeypatch, mode, kind, S, nblocks, overlap):
+    """compute-sanitizer is closed on the GPU pool (profiles/sanitizer_r2.txt); its memcheck is replaced by canary zones
+    around every device allocation of the chain (SDRB_GUARD=1): after a run on ragged stream counts no kernel may have written
+    outside its buffers, and the results must still equal the oracle's."""
+    monkeypatch.setenv("SDRB_GUARD", "1")
+    iq = station_iq(0, mode, nblocks)
+    want = oracle.chain(mode, kind, iq)
+    with capi.Chain(mode, kind, n_streams=S) as ch:
+        ch.set_overlap(overlap)
+        bb = ch.info.block_bytes
+        pcm = []
+        for b in range(nblocks):
+            ch.process_host(np.ascontiguousarray(np.stack([iq[b * bb:(b + 1) * bb]] * S)))
+            pcm.append(ch.read_pcm()[S - 1].copy())
+        assert ch.check_guards() >= 8
+    assert np.array_equal(np.concatenate(pcm), want["pcm"])
+    monkeypatch.delenv("SDRB_GUARD")
+    with capi.Chain(mode, kind, n_streams=1) as ch:
+        with pytest.raises(capi.SdrError):
+            ch.check_guards()

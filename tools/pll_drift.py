@@ -22,12 +22,12 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as g  # noqa: E402
 
 
-def patch(blob: bytes, S: int, n0: float) -> bytes:
-    off = 32 + S * 224 + S * 4 * (160 + 160 + 4 + 4 + 112 + 112)
+def patch(ch, blob: bytes, S: int, n0: float) -> bytes:
+    offs = (ch.state_item_offset("pll19"), ch.state_item_offset("pll114"))
     out = bytearray(blob)
     for which, freq in ((0, 19e3), (1, 114e3)):
         for s in range(S):
-            o = off + (which * S + s) * 24
+            o = offs[which] + s * 24
             fbI, fbQ, integ, phase, trig = struct.unpack_from("<4fd", out, o)
             th = np.float32(2 * np.pi * float(np.float32(freq) / np.float32(240000.0)) * (n0 + 13 * s) + phase)
             struct.pack_into("<4fd", out, o, float(np.float32(np.cos(np.float64(th)))), float(np.float32(np.sin(np.float64(th)))),
@@ -56,7 +56,7 @@ def main():
     rows = []
     for n0 in (0.0, 1e5, 1e6, 4e6, 1.7e7, 3.4e7, 6.8e7, 1.4e8, 2.8e8, 5.6e8, 9e8, 1.2e9, 2.5e9):
         with capi.Chain(0, "r", n_streams=S) as ch:
-            ch.state_load(patch(ch.state_save(), S, n0))
+            ch.state_load(patch(ch, ch.state_save(), S, n0))
             ch.process_device(dev_in[0].data_ptr(), pitch)  # the first block after a load takes the careful path once per lane
             ch.sync()
             r0 = ch.pll_redos()
