@@ -116,6 +116,34 @@ typedef struct {
 int sdrb_frame_sync(const int32_t* d_bits, size_t bits_pitch, const int32_t* d_nbits, int max_nbits, sdrb_framesync_state* d_state,
                     uint64_t* d_groups, size_t groups_pitch, int32_t* d_ngroups, int max_groups, int n_streams, void* stream);
 
+/* error_detection(reg, chars, output, first_time, sync, prevsync, ..., decoded_bits) - include/rds_utilities.h:14,
+ * src/rds_utilities.cpp:202-311 (with calc_syndrome :90-109): the sync-state-machine decoder the reference declares and
+ * defines but never calls (src/rds.cpp:177-179 is commented out).  The d_nbits[s] (<= max_nbits <= 8160) bits of each stream
+ * go through it; the state mirrors the function's reference parameters (a zero-initialised state is src/rds.cpp:67-84).
+ * d_events [n_streams][events_pitch] receives what the reference prints, as records: type 1 "Sync State Detected"
+ * (a = matched offset 0 A 1 B 2 C 3 D 4 C', b = number of the next block), 2 "Lost Sync (Got a bad blocks on b total)",
+ * 3 "Still Sync-ed (Got a ... b ...)", 4 the function's call of parse(value) (it makes exactly one, with a register that
+ * holds a single block: `registr` restarts at zero for every block, :280), all with bit = rds_bit_cont at that moment.
+ * EXTENSION beyond the reference: type 5 carries value = A|B|C|D of every group whose four blocks passed the check in
+ * order (what `registr` was meant to collect); feed it to sdrb_rds_parse.  d_nevents [n_streams] may exceed max_events
+ * (only the first max_events are stored).  d_syndromes (may be NULL) [n_streams][bits_pitch] receives calc_syndrome(reg, 26)
+ * after every bit (the value of the reference's per-bit debug line while it searches for sync). */
+typedef struct {
+    uint64_t reg;
+    int32_t sync, prevsync, lastseen_offset, rds_bit_cont, lastseen_offset_cont, block_distance, block_number, block_bit_cont,
+        blocks_cont, wrong_blocks_cont, group_assembly_started, group_good_blocks_cont;
+    uint64_t ext_reg; /* extension state: group register, blocks of the current group that passed */
+    int32_t ext_good;
+    int32_t reserved;
+} sdrb_rds_sync_state;
+typedef struct {
+    int32_t type, bit, a, b;
+    uint64_t value;
+} sdrb_rds_sync_event;
+int sdrb_rds_sync(const int32_t* d_bits, size_t bits_pitch, const int32_t* d_nbits, int max_nbits, sdrb_rds_sync_state* d_state,
+                  sdrb_rds_sync_event* d_events, size_t events_pitch, int32_t* d_nevents, int max_events, uint16_t* d_syndromes,
+                  int n_streams, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3. The fused receive chain: RF_frontend + mono|stereo + rds for n_streams stations
  *    (include/rffrontend.h:5, mono.h:5, stereo.h:4, rds.h:4; struct args, include/args.h:6-19).

@@ -46,6 +46,21 @@ class SyncState(C.Structure):
                 ("output", C.c_uint64), ("first_time", C.c_int), ("window", C.c_int * 4), ("nwindow", C.c_int)]
 
 
+class ErrdetState(C.Structure):
+    _fields_ = [("reg", C.c_uint64), ("chars", C.c_uint64), ("output", C.c_uint64), ("first_time", C.c_int), ("hex", C.c_int)] + \
+               [(n, C.c_int) for n in ("sync", "prevsync", "lastseen_offset", "rds_bit_cont", "lastseen_offset_cont", "block_distance",
+                                       "block_number", "block_bit_cont", "blocks_cont", "wrong_blocks_cont", "group_assembly_started",
+                                       "group_good_blocks_cont")]
+
+
+class ErrdetEvent(C.Structure):
+    _fields_ = [("type", C.c_int), ("bit", C.c_int), ("a", C.c_int), ("b", C.c_int), ("value", C.c_uint64)]
+
+
+ERRDET_STATE_NAMES = ("sync", "prevsync", "lastseen_offset", "rds_bit_cont", "lastseen_offset_cont", "block_distance", "block_number",
+                      "block_bit_cont", "blocks_cont", "wrong_blocks_cont", "group_assembly_started", "group_good_blocks_cont")
+
+
 class ChainInfo(C.Structure):
     _fields_ = [("mode", C.c_int), ("type", C.c_int), ("block_pairs", C.c_int), ("if_block", C.c_int),
                 ("audio_block", C.c_int), ("rds_block", C.c_int)]
@@ -206,6 +221,30 @@ class Oracle:
         return (np.array(groups, np.uint64), np.array(per_call, np.int32), text.value.decode("latin-1"),
                 (st.reg, st.chars, st.output), carry)
 
+    def error_detection(self, chunks, debug_lines=True):
+        """The reference's never-called sync-state-machine decoder (src/rds_utilities.cpp:202-311) over bit chunks.
+        Returns (events [(type, bit, a, b, value)], text, state64 (reg, chars, output), state dict, n_unsynced)."""
+        L = self.lib
+        L.orc_errdet_init.argtypes = [C.POINTER(ErrdetState)]
+        L.orc_error_detection.argtypes = [C.POINTER(ErrdetState), _i32p, C.c_int, C.POINTER(ErrdetEvent), C.c_int, C.c_char_p, C.c_int,
+                                          C.c_int, C.POINTER(C.c_longlong)]
+        L.orc_error_detection.restype = C.c_int
+        st = ErrdetState()
+        L.orc_errdet_init(C.byref(st))
+        total = int(sum(len(c) for c in chunks))
+        text = C.create_string_buffer(max(1 << 16, 80 * total + 4096))
+        nun = C.c_longlong(0)
+        events = []
+        for ch in chunks:
+            ch = np.ascontiguousarray(ch, np.int32)
+            cap = ch.size // 26 + 8
+            ev = (ErrdetEvent * cap)()
+            n = L.orc_error_detection(C.byref(st), ch, ch.size, ev, cap, text, len(text), 1 if debug_lines else 0, C.byref(nun))
+            assert n <= cap
+            events.extend((e.type, e.bit, e.a, e.b, e.value) for e in ev[:n])
+        state = {k: getattr(st, k) for k in ERRDET_STATE_NAMES}
+        return events, text.value, (st.reg, st.chars, st.output), state, nun.value
+
     def parse_groups(self, regs):
         chars, output = C.c_uint64(0), C.c_uint64(0)
         text = C.create_string_buffer(1 << 16)
@@ -311,6 +350,10 @@ class RefHarness:
             recfile.write(inp, recs)
             self._run(["op", inp, out])
             return recfile.read(out)
+
+    def error_detection(self, chunks) -> dict:
+        bits = np.concatenate([np.asarray(c, np.int32) for c in chunks]) if len(chunks) else np.zeros(0, np.int32)
+        return self.op("errdet", bits=bits, lens=np.array([len(c) for c in chunks], np.int32))
 
     def chain(self, mode: int, kind: str, iq: np.ndarray, stages=(), max_blocks=None) -> dict:
         with tempfile.TemporaryDirectory() as d:

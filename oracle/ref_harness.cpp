@@ -517,6 +517,32 @@ int cmd_op(const std::string& in_path, const std::string& out_path) {
         w.put("carry", carry);
         return 0;
     }
+    if (op == "errdet") {
+        // the reference's sync-state-machine decoder (declared in include/rds_utilities.h:14, defined in
+        // src/rds_utilities.cpp:202-311, never called by the reference itself): bits handed over chunk by chunk
+        std::vector<int32_t> bitv = m.at("bits").vec<int32_t>(), lens = m.at("lens").vec<int32_t>();
+        uint64_t reg = 0, chars = 0, output = 0;
+        bool first_time = true;
+        int sync = 0, prevsync = 0, lastseen_offset = 0, rds_bit_cont = 0, lastseen_offset_cont = 0, block_distance = 0,
+            block_number = 0, block_bit_cont = 0, block_cont = 0, wrong_blocks_cont = 0, group_assembly_started = 0,
+            group_good_blocks_conts = 0;  // src/rds.cpp:67-84
+        CerrCapture text;
+        size_t pos = 0;
+        for (size_t b = 0; b < lens.size(); b++) {
+            std::vector<int> chunk(bitv.begin() + pos, bitv.begin() + pos + lens[b]);
+            pos += lens[b];
+            error_detection(reg, chars, output, first_time, sync, prevsync, lastseen_offset, rds_bit_cont, lastseen_offset_cont,
+                            block_distance, block_number, block_bit_cont, block_cont, wrong_blocks_cont, group_assembly_started,
+                            group_good_blocks_conts, chunk);
+        }
+        w.put("text", text.os.str());
+        std::vector<uint64_t> st = {reg, chars, output};
+        w.put("state64", st);
+        std::vector<int32_t> sti = {sync, prevsync, lastseen_offset, rds_bit_cont, lastseen_offset_cont, block_distance, block_number,
+                                    block_bit_cont, block_cont, wrong_blocks_cont, group_assembly_started, group_good_blocks_conts};
+        w.put("state", sti);
+        return 0;
+    }
     throw std::runtime_error("unknown op " + op);
 }
 

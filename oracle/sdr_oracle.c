@@ -330,6 +330,161 @@ int orc_parse(uint64_t bytes, uint64_t* chars, uint64_t* output, char* text, int
     return pos - start;
 }
 
+/* src/rds_utilities.cpp:90-109: remainder of x(z) z^10 modulo g(z) = z^10+z^8+z^7+z^5+z^4+z^3+1 (0x5B9), mlen message bits. */
+uint64_t orc_calc_syndrome(uint64_t x, uint64_t mlen) {
+    uint64_t reg = 0;
+    const uint64_t plen = 10;
+    for (int i = (int)mlen; i > 0; i--) {
+        reg = (reg << 1) | ((x >> (i - 1)) & 0x01);
+        if (reg & (1u << plen)) reg ^= 0x5B9;
+    }
+    for (int i = (int)plen; i > 0; i--) {
+        reg <<= 1;
+        if (reg & (1u << plen)) reg ^= 0x5B9;
+    }
+    return reg & ((1u << plen) - 1);
+}
+
+void orc_errdet_init(orc_errdet_state* st) {
+    memset(st, 0, sizeof *st);
+    st->first_time = 1; /* src/rds.cpp:70 */
+}
+
+/* src/rds_utilities.cpp:202-311, statement for statement (the reference never calls it; kept as written, quirks included:
+ * `registr` is a local that restarts at 0 for every block, group_good_blocks_cont is never reset, so parse() runs once). */
+int orc_error_detection(orc_errdet_state* st, const int* bits, int nbits, orc_errdet_event* events, int max_events,
+                        char* text, int text_cap, int debug_lines, long long* n_unsynced) {
+    static const uint64_t syndromes[5] = {383, 14, 303, 663, 748};
+    static const uint64_t offset_word[5] = {252, 408, 360, 436, 848};
+    static const int offset_pos[5] = {0, 1, 2, 3, 2};
+    int nev = 0;
+    int pos = text ? (int)strlen(text) : 0;
+    char line[128];
+#define ORC_EVENT(t, aa, bb, vv)                                                    \
+    do {                                                                            \
+        if (nev < max_events) {                                                     \
+            events[nev].type = (t); events[nev].bit = st->rds_bit_cont;             \
+            events[nev].a = (aa); events[nev].b = (bb); events[nev].value = (vv);   \
+        }                                                                           \
+        nev++;                                                                      \
+    } while (0)
+    for (int i = 0; i < nbits; i++) {
+        st->reg = (st->reg << 1) | (uint64_t)bits[i]; /* :210, bits are 0/1 ints */
+        if (!st->sync) {
+            uint64_t reg_syndrome = orc_calc_syndrome(st->reg, 26);
+            if (n_unsynced) (*n_unsynced)++;
+            if (debug_lines) {
+                snprintf(line, sizeof line, st->hex ? "Reg Syndrome: %llx    Reg: %llx\n" : "Reg Syndrome: %llu    Reg: %llu\n",
+                         (unsigned long long)reg_syndrome, (unsigned long long)st->reg);
+                pos = text_append(text, text_cap, pos, line);
+            }
+            for (int j = 0; j < 5; j++) {
+                if (reg_syndrome == syndromes[j]) {
+                    if (!st->prevsync) {
+                        st->lastseen_offset = j;
+                        st->lastseen_offset_cont = st->rds_bit_cont;
+                        st->prevsync = 1;
+                    } else {
+                        if (offset_pos[st->lastseen_offset] >= offset_pos[j])
+                            st->block_distance = offset_pos[j] + 4 - offset_pos[st->lastseen_offset];
+                        else
+                            st->block_distance = offset_pos[j] - offset_pos[st->lastseen_offset];
+                        if ((st->block_distance * 26) != (st->rds_bit_cont - st->lastseen_offset_cont)) {
+                            st->prevsync = 0;
+                        } else {
+                            pos = text_append(text, text_cap, pos, "Sync State Detected\n");
+                            st->wrong_blocks_cont = 0;
+                            st->blocks_cont = 0;
+                            st->block_bit_cont = 0;
+                            st->block_number = (j + 1) & 0x03;
+                            st->group_assembly_started = 0;
+                            st->sync = 1;
+                            ORC_EVENT(1, j, st->block_number, 0);
+                        }
+                    }
+                    break;
+                }
+            }
+        } else {
+            if (st->block_bit_cont < 25) {
+                st->block_bit_cont++;
+            } else {
+                int good_block = 0;
+                uint64_t dataword = (st->reg >> 10) & 0xffff;
+                uint64_t block_calculated_crc = orc_calc_syndrome(dataword, 16);
+                uint64_t checkword = st->reg & 0x3ff;
+                uint64_t block_recieved_crc;
+                if (st->block_number == 2) {
+                    block_recieved_crc = checkword ^ offset_word[st->block_number];
+                    if (block_recieved_crc == block_calculated_crc) {
+                        good_block = 1;
+                    } else {
+                        block_recieved_crc = checkword ^ offset_word[4];
+                        if (block_recieved_crc == block_calculated_crc) {
+                            good_block = 1;
+                        } else {
+                            st->wrong_blocks_cont++;
+                            good_block = 0;
+                        }
+                    }
+                } else {
+                    block_recieved_crc = checkword ^ offset_word[st->block_number];
+                    if (block_recieved_crc == block_calculated_crc) {
+                        good_block = 1;
+                    } else {
+                        st->wrong_blocks_cont++;
+                        good_block = 0;
+                    }
+                }
+                uint64_t registr = 0;
+                if ((st->block_number == 0) & good_block) {
+                    st->group_assembly_started = 1;
+                    st->group_good_blocks_cont++;
+                }
+                if (st->group_assembly_started) {
+                    if (!good_block) {
+                        st->group_assembly_started = 0;
+                    } else {
+                        /* :285  registr &= (~(0xFFFF) << (48-block_number*16));  ~(0xFFFF) is an int (-65536), shifted as int,
+                         * then widened: on the zero register the AND does nothing either way */
+                        registr |= (dataword << (48 - st->block_number * 16));
+                        st->group_good_blocks_cont++;
+                    }
+                    if (st->group_good_blocks_cont == 5) {
+                        ORC_EVENT(4, 0, 0, registr);
+                        orc_parse(registr, &st->chars, &st->output, text, text_cap); /* appends at strlen(text) == pos */
+                        pos = text ? (int)strlen(text) : 0;
+                        st->hex = 1; /* parse() leaves std::hex set on std::cerr (:180): every later number prints in hex */
+                    }
+                }
+                st->block_bit_cont = 0;
+                st->block_number = (st->block_number + 1) & 0x03;
+                st->blocks_cont++;
+                if (st->blocks_cont == 50) {
+                    if (st->wrong_blocks_cont > 40) {
+                        snprintf(line, sizeof line, st->hex ? "Lost Sync (Got %x bad blocks on %x total)\n" : "Lost Sync (Got %d bad blocks on %d total)\n",
+                                 st->wrong_blocks_cont, st->blocks_cont);
+                        pos = text_append(text, text_cap, pos, line);
+                        ORC_EVENT(2, st->wrong_blocks_cont, st->blocks_cont, 0);
+                        st->sync = 0;
+                        st->prevsync = 0;
+                    } else {
+                        snprintf(line, sizeof line, st->hex ? "Still Sync-ed (Got %x bad blocks on %x total)\n" : "Still Sync-ed (Got %d bad blocks on %d total)\n",
+                                 st->wrong_blocks_cont, st->blocks_cont);
+                        pos = text_append(text, text_cap, pos, line);
+                        ORC_EVENT(3, st->wrong_blocks_cont, st->blocks_cont, 0);
+                    }
+                    st->blocks_cont = 0;
+                    st->wrong_blocks_cont = 0;
+                }
+            }
+        }
+        st->rds_bit_cont++;
+    }
+#undef ORC_EVENT
+    return nev;
+}
+
 /* src/rds_utilities.cpp:384-400 with check_block (:352-381), uint_copy (:313-337) and
  * isSequenceABCD (:339-350) folded in.  Note `idx < size-26` (strict): the last full window of a
  * call is never tested, it is carried into the next call instead. */

@@ -73,6 +73,31 @@ int orc_frame_sync(orc_sync_state* st, const int* bits, int nbits, uint64_t* gro
 /* parse (:172-199) on one group register; appends to text; returns bytes written */
 int orc_parse(uint64_t reg, uint64_t* chars, uint64_t* output, char* text, int text_cap);
 
+/* ---- error_detection, the sync-state-machine decoder the reference declares (include/rds_utilities.h:14) and defines
+ * (src/rds_utilities.cpp:202-311, calc_syndrome :90-109) but never calls (src/rds.cpp:177-179 is commented out) ---- */
+typedef struct {
+    uint64_t reg, chars, output;
+    int first_time;
+    int hex; /* std::hex is sticky on std::cerr once parse() ran (src/rds_utilities.cpp:180) */
+    int sync, prevsync, lastseen_offset, rds_bit_cont, lastseen_offset_cont, block_distance, block_number, block_bit_cont,
+        blocks_cont, wrong_blocks_cont, group_assembly_started, group_good_blocks_cont;
+} orc_errdet_state;
+typedef struct {
+    int type;       /* 1 "Sync State Detected" (a = matched offset 0 A 1 B 2 C 3 D 4 C', b = next block number),
+                       2 "Lost Sync" (a wrong, b total), 3 "Still Sync-ed" (a wrong, b total), 4 parse(registr) (value) */
+    int bit;        /* rds_bit_cont when it happened */
+    int a, b;
+    uint64_t value;
+} orc_errdet_event;
+void orc_errdet_init(orc_errdet_state* st);  /* the initial values of src/rds.cpp:67-86 */
+uint64_t orc_calc_syndrome(uint64_t x, uint64_t mlen);
+/* One error_detection call over nbits bits.  events (max_events entries) receives what happened; text (may be NULL)
+ * what the reference prints on stderr, the per-bit "Reg Syndrome" debug lines included when debug_lines != 0;
+ * *n_unsynced (may be NULL) is incremented by the number of bits processed out of sync (= debug lines).
+ * Returns the number of events. */
+int orc_error_detection(orc_errdet_state* st, const int* bits, int nbits, orc_errdet_event* events, int max_events,
+                        char* text, int text_cap, int debug_lines, long long* n_unsynced);
+
 /* ---- whole receive chain, one stream (src/rffrontend.cpp, mono.cpp, stereo.cpp, rds.cpp) ---- */
 typedef struct orc_chain orc_chain;
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "sdrb_manchester_decode", "sdrb_differential_decode", "sdrb_frame_sync",
     "sdrb_chain_state_load_n", "sdrb_chain_input_consumed", "sdrb_chain_rds_overflows",
     "sdrb_chain_pll_redos", "sdrb_chain_pll_redo_detail", "sdrb_chain_check_guards",
-    "sdrb_chain_state_item_offset",
+    "sdrb_chain_state_item_offset", "sdrb_rds_sync",
 ]
 
 
@@ -51,6 +51,12 @@ class RdsRecord(C.Structure):
 
 MANCHESTER_STATE_DTYPE = np.dtype([("half_symbol", "<i4"), ("start", "<i4")])
 FRAMESYNC_STATE_DTYPE = np.dtype([("reg", "<u8"), ("window", "<i4", (4,)), ("nwindow", "<i4"), ("ncarry", "<i4"), ("carry", "u1", (64,))])
+RDS_SYNC_STATE_DTYPE = np.dtype([("reg", "<u8"), ("sync", "<i4"), ("prevsync", "<i4"), ("lastseen_offset", "<i4"), ("rds_bit_cont", "<i4"),
+                                 ("lastseen_offset_cont", "<i4"), ("block_distance", "<i4"), ("block_number", "<i4"), ("block_bit_cont", "<i4"),
+                                 ("blocks_cont", "<i4"), ("wrong_blocks_cont", "<i4"), ("group_assembly_started", "<i4"),
+                                 ("group_good_blocks_cont", "<i4"), ("ext_reg", "<u8"), ("ext_good", "<i4"), ("reserved", "<i4")])
+RDS_SYNC_EVENT_DTYPE = np.dtype([("type", "<i4"), ("bit", "<i4"), ("a", "<i4"), ("b", "<i4"), ("value", "<u8")])
+assert RDS_SYNC_STATE_DTYPE.itemsize == 72 and RDS_SYNC_EVENT_DTYPE.itemsize == 24
 RDS_RECORD_DTYPE = np.dtype([("cdr_offset", "<i4"), ("n_symbols", "<i4"), ("n_bits", "<i4"), ("n_groups", "<i4"),
                              ("bits", "u1", (48,)), ("groups", "<u8", (8,))])
 assert RDS_RECORD_DTYPE.itemsize == C.sizeof(RdsRecord)
@@ -96,6 +102,7 @@ def load(path: str | None = None) -> C.CDLL:
     L.sdrb_manchester_decode.argtypes = [vp, sz, vp, ci, vp, vp, sz, vp, ci, vp]
     L.sdrb_differential_decode.argtypes = [vp, sz, vp, ci, vp, vp, sz, ci, vp]
     L.sdrb_frame_sync.argtypes = [vp, sz, vp, ci, vp, vp, sz, vp, ci, ci, vp]
+    L.sdrb_rds_sync.argtypes = [vp, sz, vp, ci, vp, vp, sz, vp, ci, vp, ci, vp]
     L.sdrb_config_for_mode.argtypes = [ci, ci, ci, C.POINTER(Config)]
     L.sdrb_chain_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     L.sdrb_chain_destroy.argtypes = [vp]

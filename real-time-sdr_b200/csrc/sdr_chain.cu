@@ -1254,4 +1254,18 @@ int sdrb_frame_sync(const int32_t* d_bits, size_t bits_pitch, const int32_t* d_n
     return SDRB_OK;
 }
 
+int sdrb_rds_sync(const int32_t* d_bits, size_t bits_pitch, const int32_t* d_nbits, int max_nbits, sdrb_rds_sync_state* d_state,
+                  sdrb_rds_sync_event* d_events, size_t events_pitch, int32_t* d_nevents, int max_events, uint16_t* d_syndromes,
+                  int n_streams, void* stream) {
+    if (!d_bits || !d_nbits || !d_state || !d_events || !d_nevents || max_events < 0 || n_streams < 1) return fail(SDRB_ERR_INVALID, "bad argument");
+    if (max_nbits < 0 || max_nbits + 32 > kFrameSyncMaxBits) return fail(SDRB_ERR_INVALID, "sdrb_rds_sync: at most 8160 bits per call");
+    static_assert(sizeof(sdrb_rds_sync_state) == sizeof(RdsSyncState), "ABI struct");
+    static_assert(sizeof(sdrb_rds_sync_event) == sizeof(RdsSyncEvent), "ABI struct");
+    k_rds_sync_generic<<<n_streams, 32, 0, (cudaStream_t)stream>>>(d_bits, bits_pitch, d_nbits, reinterpret_cast<RdsSyncState*>(d_state),
+                                                                    reinterpret_cast<RdsSyncEvent*>(d_events), events_pitch, d_nevents, max_events,
+                                                                    reinterpret_cast<unsigned short*>(d_syndromes));
+    CU(cudaGetLastError());
+    return SDRB_OK;
+}
+
 }  // extern "C"

@@ -1017,7 +1017,11 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
         float2 acc[kResQ / 2];
 #pragma unroll
         for (int pq = 0; pq < kResQ / 2; pq++) acc[pq] = make_float2(0.0f, 0.0f);
-#pragma unroll 3
+#ifndef SDRB_RES_UNROLL
+#define SDRB_RES_UNROLL 17
+#endif
+        constexpr int kResUnroll = SDRB_RES_UNROLL;  // tap loads in flight ahead of their MACs
+#pragma unroll kResUnroll
         for (int i = 0; i < kResGroups; i++) {
             const float2 h = __ldg(a.taps_pair + i * 256 + t);
 #pragma unroll
@@ -1455,6 +1459,176 @@ __global__ void __launch_bounds__(32) k_frame_sync_generic(const int32_t* bits, 
         for (int i = 0; i < keep; i++) st->carry[i] = (uint8_t)((sbuf[(idx + i) >> 5] >> ((idx + i) & 31)) & 1u);
         st->ncarry = keep;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// error_detection: the sync-state-machine RDS decoder the reference declares (include/rds_utilities.h:14) and defines
+// (/root/reference/src/rds_utilities.cpp:202-311, calc_syndrome :90-109) but never calls (src/rds.cpp:177-179 is commented
+// out).  One warp per stream: the two linear maps of every 26-bit window of the call - the syndrome calc_syndrome(reg, 26)
+// = w(z) z^10 mod g(z) that the search for sync compares with the five offset syndromes, and the remainder w(z) mod g(z)
+// that the block check of the locked state needs (checkword ^ offset == calc_syndrome(dataword, 16)  <=>  w mod g == offset)
+// - are taken in parallel as popcount parities; lane 0 then walks the bits through the reference's state machine, one
+// table look-up per bit.  Besides the reference's own observable events (sync found / kept / lost, its one parse() call)
+// the walk assembles groups the way the reference meant to (its `registr` is a local that restarts at zero for every
+// block): event 5 carries A|B|C|D of every group whose four blocks passed the check in order.
+// ------------------------------------------------------------------------------------------------
+struct RdsSyncState {  // mirrors sdrb_rds_sync_state
+    uint64_t reg;
+    int32_t sync, prevsync, lastseen_offset, rds_bit_cont, lastseen_offset_cont, block_distance, block_number, block_bit_cont,
+        blocks_cont, wrong_blocks_cont, group_assembly_started, group_good_blocks_cont;
+    uint64_t ext_reg;   // extension: group register that persists across the blocks of a group
+    int32_t ext_good;   // extension: blocks 0..ext_good-1 of the current group passed the check
+    int32_t reserved;
+};
+struct RdsSyncEvent {  // mirrors sdrb_rds_sync_event
+    int32_t type, bit, a, b;
+    uint64_t value;
+};
+
+__host__ __device__ constexpr uint32_t rds_zpow_mod_g(int e) {  // z^e mod g(z), g = 0x5B9
+    uint32_t v = 1;
+    for (int i = 0; i < e; i++) {
+        v <<= 1;
+        if (v & 0x400u) v ^= 0x5B9u;
+    }
+    return v;
+}
+// parity mask of output bit c of the map  w -> w(z) z^shift mod g(z)  over the 26 window bits (bit t of w = coefficient of z^t)
+__host__ __device__ constexpr uint32_t rds_row_mask(int c, int shift) {
+    uint32_t m = 0;
+    for (int t = 0; t < 26; t++) m |= ((rds_zpow_mod_g(t + shift) >> c) & 1u) << t;
+    return m;
+}
+template <int SHIFT>
+__device__ __forceinline__ uint32_t rds_window_map(uint32_t w) {
+    constexpr uint32_t rows[10] = {rds_row_mask(0, SHIFT), rds_row_mask(1, SHIFT), rds_row_mask(2, SHIFT), rds_row_mask(3, SHIFT),
+                                   rds_row_mask(4, SHIFT), rds_row_mask(5, SHIFT), rds_row_mask(6, SHIFT), rds_row_mask(7, SHIFT),
+                                   rds_row_mask(8, SHIFT), rds_row_mask(9, SHIFT)};
+    uint32_t v = 0;
+#pragma unroll
+    for (int c = 0; c < 10; c++) v |= (uint32_t)(__popc(w & rows[c]) & 1) << c;
+    return v;
+}
+
+__global__ void __launch_bounds__(32) k_rds_sync_generic(const int32_t* bits, size_t bits_pitch, const int32_t* nbits, RdsSyncState* state,
+                                                         RdsSyncEvent* events, size_t events_pitch, int32_t* nevents, int max_events,
+                                                         unsigned short* syndromes) {
+    __shared__ uint32_t sbuf[kFrameSyncMaxBits / 32 + 3];
+    __shared__ unsigned short sS[kFrameSyncMaxBits], sR[kFrameSyncMaxBits];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int32_t* b = bits + (size_t)s * bits_pitch;
+    RdsSyncState* stp = state + s;
+    const int n = min(max(nbits[s], 0), kFrameSyncMaxBits - 32);
+    const uint64_t reg0 = stp->reg;
+    // bit p of the buffer: p < 25 the 25 bits before this call (oldest first), then the new bits
+    for (int w = lane; w < kFrameSyncMaxBits / 32 + 3; w += 32) sbuf[w] = 0u;
+    __syncwarp();
+    for (int p0 = 0; p0 < n + 25; p0 += 32) {
+        const int p = p0 + lane;
+        int v = 0;
+        if (p < 25) v = (int)((reg0 >> (24 - p)) & 1ull);
+        else if (p < n + 25) v = b[p - 25] != 0;
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, v != 0);
+        if (lane == 0) sbuf[p0 >> 5] = word;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        // window of new bit i: buffer bits i .. i+25, oldest first; as a polynomial the newest bit is the constant term
+        const int wd = i >> 5, sh = i & 31;
+        const uint64_t two = (uint64_t)sbuf[wd] | ((uint64_t)sbuf[wd + 1] << 32);
+        const uint32_t w = __brev((uint32_t)(two >> sh) & 0x3FFFFFFu) >> 6;
+        const uint32_t S = rds_window_map<10>(w), R = rds_window_map<0>(w);
+        sS[i] = (unsigned short)S;
+        sR[i] = (unsigned short)R;
+        if (syndromes) syndromes[(size_t)s * bits_pitch + i] = (unsigned short)S;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    RdsSyncState st = *stp;
+    RdsSyncEvent* ev = events + (size_t)s * events_pitch;
+    int nev = 0;
+    auto emit = [&](int type, int a, int bb, uint64_t value) {
+        if (nev < max_events) ev[nev] = RdsSyncEvent{type, st.rds_bit_cont, a, bb, value};
+        nev++;
+    };
+    const int syn_of[5] = {383, 14, 303, 663, 748};          // A, B, C, D, C'   (:205)
+    const int offset_word[5] = {252, 408, 360, 436, 848};    // (:206)
+    const int offset_pos[5] = {0, 1, 2, 3, 2};               // (:207)
+    for (int i = 0; i < n; i++) {
+        st.reg = (st.reg << 1) | (uint64_t)((sbuf[(i + 25) >> 5] >> ((i + 25) & 31)) & 1u);
+        if (!st.sync) {
+            const int S = sS[i];
+            for (int j = 0; j < 5; j++) {
+                if (S != syn_of[j]) continue;
+                if (!st.prevsync) {
+                    st.lastseen_offset = j;
+                    st.lastseen_offset_cont = st.rds_bit_cont;
+                    st.prevsync = 1;
+                } else {
+                    st.block_distance = offset_pos[st.lastseen_offset] >= offset_pos[j] ? offset_pos[j] + 4 - offset_pos[st.lastseen_offset]
+                                                                                       : offset_pos[j] - offset_pos[st.lastseen_offset];
+                    if (st.block_distance * 26 != st.rds_bit_cont - st.lastseen_offset_cont) {
+                        st.prevsync = 0;
+                    } else {
+                        st.wrong_blocks_cont = 0;
+                        st.blocks_cont = 0;
+                        st.block_bit_cont = 0;
+                        st.block_number = (j + 1) & 3;
+                        st.group_assembly_started = 0;
+                        st.sync = 1;
+                        st.ext_good = 0;
+                        emit(1, j, st.block_number, 0);
+                    }
+                }
+                break;
+            }
+        } else if (st.block_bit_cont < 25) {
+            st.block_bit_cont++;
+        } else {
+            const int R = sR[i];
+            const uint64_t dataword = (st.reg >> 10) & 0xFFFFull;
+            const int bn = st.block_number;
+            const bool good = R == offset_word[bn] || (bn == 2 && R == offset_word[4]);
+            if (!good) st.wrong_blocks_cont++;
+            uint64_t registr = 0;
+            if (bn == 0 && good) {
+                st.group_assembly_started = 1;
+                st.group_good_blocks_cont++;
+            }
+            if (st.group_assembly_started) {
+                if (!good) {
+                    st.group_assembly_started = 0;
+                } else {
+                    registr |= dataword << (48 - bn * 16);
+                    st.group_good_blocks_cont++;
+                }
+                if (st.group_good_blocks_cont == 5) emit(4, 0, 0, registr);
+            }
+            // extension: the group register the reference meant to keep
+            if (!good) st.ext_good = 0;
+            else if (bn == 0) { st.ext_reg = dataword << 48; st.ext_good = 1; }
+            else if (st.ext_good == bn) { st.ext_reg |= dataword << (48 - bn * 16); st.ext_good++; }
+            else st.ext_good = 0;
+            if (bn == 3 && st.ext_good == 4) { emit(5, 0, 0, st.ext_reg); st.ext_good = 0; }
+            st.block_bit_cont = 0;
+            st.block_number = (bn + 1) & 3;
+            st.blocks_cont++;
+            if (st.blocks_cont == 50) {
+                if (st.wrong_blocks_cont > 40) {
+                    emit(2, st.wrong_blocks_cont, st.blocks_cont, 0);
+                    st.sync = 0;
+                    st.prevsync = 0;
+                } else {
+                    emit(3, st.wrong_blocks_cont, st.blocks_cont, 0);
+                }
+                st.blocks_cont = 0;
+                st.wrong_blocks_cont = 0;
+            }
+        }
+        st.rds_bit_cont++;
+    }
+    *stp = st;
+    nevents[s] = nev;
 }
 
 }  // namespace sdrb

@@ -174,7 +174,62 @@ void parse(uint64_t bytes, uint64_t& chars, uint64_t& output, bool& first_time) 
     char text[256];
     sdrb_rds_parse(bytes, &chars, &output, text, sizeof text);
     std::cerr << text;
+    std::cerr << std::hex;  // the reference's parse() leaves std::hex set on std::cerr (src/rds_utilities.cpp:180): numbers printed later are hex
     (void)first_time;  // the reference writes it after the first group and never reads it again
+}
+
+// include/rds_utilities.h:14, src/rds_utilities.cpp:202-311.  The state machine runs on the GPU (sdrb_rds_sync, one warp
+// per stream); what the reference prints on std::cerr is replayed here from the events and per-bit syndromes it returns.
+void error_detection(uint64_t& reg, uint64_t& chars, uint64_t& output, bool& first_time, int& sync, int& prevsync, int& lastseen_offset,
+                     int& rds_bit_cont, int& lastseen_offset_cont, int& block_distance, int& block_number, int& block_bit_cont, int& blocks_cont,
+                     int& wrong_blocks_cont, int& group_assembly_started, int& group_good_blocks_cont, const std::vector<int>& decoded_bits) {
+    size_t done = 0;
+    while (done < decoded_bits.size()) {  // the device entry point takes at most 8160 bits per call
+        const size_t n = std::min<size_t>(decoded_bits.size() - done, 8160);
+        sdrb_rds_sync_state st{};
+        st.reg = reg; st.sync = sync; st.prevsync = prevsync; st.lastseen_offset = lastseen_offset; st.rds_bit_cont = rds_bit_cont;
+        st.lastseen_offset_cont = lastseen_offset_cont; st.block_distance = block_distance; st.block_number = block_number;
+        st.block_bit_cont = block_bit_cont; st.blocks_cont = blocks_cont; st.wrong_blocks_cont = wrong_blocks_cont;
+        st.group_assembly_started = group_assembly_started; st.group_good_blocks_cont = group_good_blocks_cont;
+        const std::vector<int32_t> chunk(decoded_bits.begin() + done, decoded_bits.begin() + done + n);
+        const int32_t nb = (int32_t)n;
+        const int max_events = (int)n / 26 + 8;
+        DevBuf<int32_t> dbits(chunk.data(), n), dn(&nb, 1), dnev(1);
+        DevBuf<sdrb_rds_sync_state> dst(&st, 1);
+        DevBuf<sdrb_rds_sync_event> dev((size_t)max_events);
+        DevBuf<uint16_t> dsyn(n);
+        ok(sdrb_rds_sync(dbits.p, n, dn.p, nb, dst.p, dev.p, (size_t)max_events, dnev.p, max_events, dsyn.p, 1, nullptr));
+        cu(cudaDeviceSynchronize());
+        int32_t nev = 0;
+        dnev.to_host(&nev, 1);
+        std::vector<sdrb_rds_sync_event> ev((size_t)std::min(nev, max_events));
+        dev.to_host(ev.data(), ev.size());
+        std::vector<uint16_t> syn(n);
+        dsyn.to_host(syn.data(), n);
+        // replay of the reference's output, bit by bit: the debug line while searching, then whatever happened at that bit
+        bool in_sync = sync != 0;
+        uint64_t r = reg;
+        size_t e = 0;
+        for (size_t i = 0; i < n; i++) {
+            r = (r << 1) | (uint64_t)chunk[i];
+            if (!in_sync) std::cerr << "Reg Syndrome: " << (uint64_t)syn[i] << "    Reg: " << r << std::endl;
+            for (; e < ev.size() && ev[e].bit == rds_bit_cont + (int)i; e++) {
+                switch (ev[e].type) {
+                    case 1: std::cerr << "Sync State Detected" << std::endl; in_sync = true; break;
+                    case 2: std::cerr << "Lost Sync (Got " << ev[e].a << " bad blocks on " << ev[e].b << " total)" << std::endl; in_sync = false; break;
+                    case 3: std::cerr << "Still Sync-ed (Got " << ev[e].a << " bad blocks on " << ev[e].b << " total)" << std::endl; break;
+                    case 4: parse(ev[e].value, chars, output, first_time); break;
+                    default: break;  // type 5 (complete groups) is this library's extension: the reference prints nothing for it
+                }
+            }
+        }
+        dst.to_host(&st, 1);
+        reg = st.reg; sync = st.sync; prevsync = st.prevsync; lastseen_offset = st.lastseen_offset; rds_bit_cont = st.rds_bit_cont;
+        lastseen_offset_cont = st.lastseen_offset_cont; block_distance = st.block_distance; block_number = st.block_number;
+        block_bit_cont = st.block_bit_cont; blocks_cont = st.blocks_cont; wrong_blocks_cont = st.wrong_blocks_cont;
+        group_assembly_started = st.group_assembly_started; group_good_blocks_cont = st.group_good_blocks_cont;
+        done += n;
+    }
 }
 
 void check_block(std::string& offset_type, std::vector<int>::iterator b, std::vector<int>::iterator e, uint64_t& reg, uint64_t& chars,

@@ -59,6 +59,10 @@ void check_block(std::string& offset_type, std::vector<int>::iterator bitstream_
 void start_frame_sync(unsigned int& idx, std::vector<int>& stream, std::vector<int>& synch_state_bits, uint64_t& reg,
                       uint64_t& chars, uint64_t& output, bool& first_time, std::deque<std::string>& window);                    // :384-400
 void parse(uint64_t bytes, uint64_t& chars, uint64_t& output, bool& first_time);                                                // :172-199
+// the sync-state-machine decoder the reference declares and defines but never calls (src/rds.cpp:177-179)                      // :202-311
+void error_detection(uint64_t& reg, uint64_t& chars, uint64_t& output, bool& first_time, int& sync, int& prevsync, int& lastseen_offset,
+                     int& rds_bit_cont, int& lastseen_offset_cont, int& block_distance, int& block_number, int& block_bit_cont, int& blocks_cont,
+                     int& wrong_blocks_cont, int& group_assembly_started, int& group_good_blocks_cont, const std::vector<int>& decoded_bits);
 
 struct sdrb_chain;
 

@@ -102,6 +102,19 @@ def main():
         f["groups"], f["groups_per_call"], f["text"], f["state"], f["carry"])
     np.savez_compressed(os.path.join(HERE, "ops.npz"), **ops)
 
+    # error_detection (declared include/rds_utilities.h:14, defined src/rds_utilities.cpp:202-311, never called by the
+    # reference): the unmodified function on the streams of tests/rds_streams.py, in the chain's ragged chunks
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import rds_streams
+    ed = {}
+    for name, bits in rds_streams.cases(gen).items():
+        chunks = rds_streams.chunks_of(bits)
+        e = ref.error_detection(chunks)
+        ed[name + "_bits"] = bits.astype(np.int8)
+        ed[name + "_lens"] = np.array([len(c) for c in chunks], np.int32)
+        ed[name + "_text"], ed[name + "_state64"], ed[name + "_state"] = e["text"], e["state64"], e["state"]
+    np.savez_compressed(os.path.join(HERE, "errdet.npz"), **ed)
+
     src = open("/root/reference/test/parser_test.cpp").read()
     body = src[src.index("uint64_t regs[] = {"):]
     body = body[: body.index("};")]

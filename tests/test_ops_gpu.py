@@ -251,3 +251,89 @@ def test_frame_sync_golden_and_batch(capi, oracle, torch):
         assert np.array_equal(np.array(per_call[s], np.int32), want_calls), s
         assert int(st[s]["reg"]) == int(reg), s
         assert np.array_equal(st[s]["carry"][: st[s]["ncarry"]].astype(np.int32), carry), s
+
+
+def _run_rds_sync(capi, torch, chunks_per_stream, want_syndromes=False):
+    """sdrb_rds_sync over per-stream chunk lists (same number of calls per stream).  Returns per stream (events, state, syndromes)."""
+    L = capi.lib()
+    S = len(chunks_per_stream)
+    ncalls = max(len(c) for c in chunks_per_stream)
+    st = torch.zeros(S * capi.RDS_SYNC_STATE_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    events = [[] for _ in range(S)]
+    syn = [[] for _ in range(S)]
+    for c in range(ncalls):
+        lens = [len(chunks_per_stream[s][c]) if c < len(chunks_per_stream[s]) else 0 for s in range(S)]
+        pitch = max(lens) + 5
+        bits = np.zeros((S, pitch), np.int32)
+        for s in range(S):
+            if lens[s]:
+                bits[s, :lens[s]] = chunks_per_stream[s][c]
+        cap = max(lens) // 26 + 8
+        nb = dev(torch, np.array(lens, np.int32))
+        d_bits = dev(torch, bits)
+        ev = torch.zeros(S * cap * capi.RDS_SYNC_EVENT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        nev = torch.zeros(S, dtype=torch.int32, device="cuda")
+        d_syn = torch.zeros((S, pitch), dtype=torch.int16, device="cuda") if want_syndromes else None
+        capi.check(L.sdrb_rds_sync(d_bits.data_ptr(), pitch, nb.data_ptr(), max(lens), st.data_ptr(), ev.data_ptr(), cap, nev.data_ptr(), cap,
+                                   d_syn.data_ptr() if want_syndromes else None, S, None))
+        torch.cuda.synchronize()
+        evh = ev.cpu().numpy().view(capi.RDS_SYNC_EVENT_DTYPE).reshape(S, cap)
+        nevh = nev.cpu().numpy()
+        for s in range(S):
+            assert nevh[s] <= cap
+            events[s].extend((int(e["type"]), int(e["bit"]), int(e["a"]), int(e["b"]), int(e["value"])) for e in evh[s, :nevh[s]])
+            if want_syndromes:
+                syn[s].append(d_syn.cpu().numpy().view(np.uint16)[s, :lens[s]].copy())
+    sth = st.cpu().numpy().view(capi.RDS_SYNC_STATE_DTYPE)
+    return events, sth, syn
+
+
+def test_rds_sync_state_machine(capi, oracle, oracle_mod, sdrgen, torch):
+    """sdrb_rds_sync = the reference's error_detection (src/rds_utilities.cpp:202-311): on every stream of tests/rds_streams.py,
+    in the chain's ragged chunks and in one piece, as one ragged batch: events 1-4 and all carried state equal the oracle's
+    (which equals the unmodified reference function, tests/test_oracle_vs_ref.py and tests/golden/errdet.npz); the per-bit
+    syndromes equal calc_syndrome on the running register; the extension's events (type 5) are exactly the groups whose
+    four blocks are intact."""
+    import rds_streams
+    cases = rds_streams.cases(sdrgen)
+    names = sorted(cases)
+    per_stream = [rds_streams.chunks_of(cases[n]) for n in names]
+    per_stream += [rds_streams.chunks_of(cases[n], sizes=(701, 13, 1, 999, 2600)) for n in names]   # other chunkings, one-bit calls
+    events, st, syn = _run_rds_sync(capi, torch, per_stream, want_syndromes=True)
+    for s, chunks in enumerate(per_stream):
+        name = names[s % len(names)]
+        want_ev, _, st64, wst, nun = oracle.error_detection(chunks, debug_lines=False)
+        ref_events = [e for e in events[s] if e[0] != 5]
+        assert ref_events == [tuple(int(v) for v in e) for e in want_ev], (name, s)
+        assert int(st[s]["reg"]) == int(st64[0]), name
+        for k in oracle_mod.ERRDET_STATE_NAMES:
+            assert int(st[s][k]) == wst[k], (name, k)
+        # calc_syndrome(reg, 26) after every bit
+        bits = cases[name]
+        got = np.concatenate(syn[s])
+        reg = 0
+        for i in range(0, bits.size, 97):  # spot checks along the stream (the oracle function is scalar Python-speed)
+            reg = 0
+            for b in bits[max(0, i - 25):i + 1]:
+                reg = (reg << 1) | int(b)
+            assert int(got[i]) == int(oracle.lib.orc_calc_syndrome(reg, 26)), (name, i)
+    # the extension: complete groups.  Clean stream: every group after the sync point, in order, with the right content.
+    ext = [e[4] for e in events[names.index("clean")] if e[0] == 5]
+    words = [sdrgen.rds_group_0a(0x1234, 5, "B200-SDR", g & 3) for g in range(40)]
+    all_groups = [(w[0] << 48) | (w[1] << 32) | (w[2] << 16) | w[3] for w in words]
+    assert len(ext) >= 38 and ext == all_groups[-len(ext):]
+    dec = capi.RdsTextDecoder()
+    for g in ext:
+        dec.feed(g)
+    assert b"PI: 1234" in dec.text and b"PTY: Rock" in dec.text and b"Program Service: B200-SDR" in dec.text
+    # 1 % bit errors: fewer groups, but never a wrong one
+    ext_ber = [e[4] for e in events[names.index("ber_1pct")] if e[0] == 5]
+    assert 5 < len(ext_ber) < len(ext) and set(ext_ber) <= set(all_groups)
+    assert [e for e in events[names.index("noise")] if e[0] == 5] == []
+
+
+def test_rds_sync_argument_checks(capi, torch):
+    L = capi.lib()
+    z = torch.zeros(64, dtype=torch.int32, device="cuda")
+    assert L.sdrb_rds_sync(None, 8, z.data_ptr(), 8, z.data_ptr(), z.data_ptr(), 1, z.data_ptr(), 1, None, 1, None) == capi.SDRB_ERR_INVALID
+    assert L.sdrb_rds_sync(z.data_ptr(), 8, z.data_ptr(), 9000, z.data_ptr(), z.data_ptr(), 1, z.data_ptr(), 1, None, 1, None) == capi.SDRB_ERR_INVALID

@@ -138,3 +138,21 @@ def test_parser_registers_of_the_reference_test(oracle, capi):
     for r in regs:
         dec.feed(int(r))
     assert dec.text.decode("latin-1") == text
+
+
+def test_error_detection_fixture(oracle, sdrgen):
+    """tests/golden/errdet.npz: what the UNMODIFIED reference function error_detection (src/rds_utilities.cpp:202-311) printed
+    and left in its state variables on the streams of tests/rds_streams.py; the oracle restatement must reproduce it."""
+    import rds_streams
+    z = np.load(os.path.join(G, "errdet.npz"))
+    names = sorted(k[:-5] for k in z.files if k.endswith("_bits"))
+    assert len(names) == 5
+    for name in names:
+        chunks = np.split(z[name + "_bits"].astype(np.int32), np.cumsum(z[name + "_lens"])[:-1])
+        ev, text, st64, st, nun = oracle.error_detection(chunks)
+        assert text == bytes(z[name + "_text"]), name
+        assert [int(v) for v in st64] == [int(v) for v in z[name + "_state64"]], name
+        from conftest import load_module
+        keys = load_module("oracle_py", "oracle/oracle_py.py").ERRDET_STATE_NAMES
+        assert [st[k] for k in keys] == [int(v) for v in z[name + "_state"]], name
+        assert np.array_equal(z[name + "_bits"].astype(np.int32), rds_streams.cases(sdrgen)[name]), "the fixture's streams are those of tests/rds_streams.py"

@@ -83,3 +83,25 @@ def test_reference_rds_thread_is_silent_outside_mode0(oracle, ref, station_iq, m
     assert err == b""
     pcm = oracle.chain(mode, "s", iq)["pcm"].tobytes()
     assert len(out) >= nb * (len(pcm) // (nb + pad)) and out == pcm[: len(out)]
+
+
+def test_error_detection_state_machine(oracle, ref, sdrgen):
+    """The sync-state-machine decoder the reference declares and defines but never calls (include/rds_utilities.h:14,
+    src/rds_utilities.cpp:202-311): the restatement against the unmodified function, on clean, noisy and sync-losing bit
+    streams handed over in the chain's ragged chunks - every line it prints (the per-bit debug lines and the sticky std::hex
+    after its one parse() call included) and every state variable it leaves behind."""
+    import rds_streams
+    for name, bits in rds_streams.cases(sdrgen).items():
+        chunks = rds_streams.chunks_of(bits)
+        ev, text, st64, st, nun = oracle.error_detection(chunks)
+        r = ref.error_detection(chunks)
+        assert bytes(r["text"]) == text, name
+        assert tuple(int(v) for v in r["state64"]) == tuple(int(v) for v in st64), name
+        assert [int(v) for v in r["state"]] == [st[k] for k in oracle_names()], name
+    kinds = {e[0] for e in oracle.error_detection(rds_streams.chunks_of(rds_streams.cases(sdrgen)["burst_lose_sync"]))[0]}
+    assert {1, 2, 3} <= kinds, "the burst case must lose sync and find it again for this test to mean anything"
+
+
+def oracle_names():
+    from conftest import load_module
+    return load_module("oracle_py", "oracle/oracle_py.py").ERRDET_STATE_NAMES

@@ -56,6 +56,19 @@ def test_functions_against_golden_vectors(shim):
     assert same(f["groups"], z["fs_groups"]) and same(f["text"], z["fs_text"]) and same(f["carry"], z["fs_carry"])
 
 
+def test_error_detection_drop_in(shim):
+    """error_detection(...) with the reference's 17-argument signature (include/rds_utilities.h:14) on the GPU: the shim
+    harness calls it exactly as it calls the reference's own (oracle/ref_harness.cpp, op "errdet"); every line on stderr
+    (per-bit debug lines, sticky std::hex after parse) and every state variable must equal what the unmodified reference
+    function produced (tests/golden/errdet.npz)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "errdet.npz"))
+    for name in sorted(k[:-5] for k in z.files if k.endswith("_bits")):
+        chunks = np.split(z[name + "_bits"].astype(np.int32), np.cumsum(z[name + "_lens"])[:-1])
+        got = shim.error_detection(chunks)
+        assert bytes(got["text"]) == bytes(z[name + "_text"]), name
+        assert same(got["state64"], z[name + "_state64"]) and same(got["state"], z[name + "_state"]), name
+
+
 def test_reference_shaped_block_loop(shim, oracle, station_iq):
     """The reference's three loop bodies, restated in the harness, running on the shim's functions: every stage equal."""
     iq = station_iq(0, 0, 22)
