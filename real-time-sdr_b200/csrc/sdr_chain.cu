@@ -91,7 +91,9 @@ struct sdrb_chain {
     // taps
     Taps101 rf_h, pilot_h, stereo_h, rds_h, rds114_h, rrc_h, audio_h;
     float* d_audio_pm = nullptr;   // phase-major audio taps (up > 1)
-    float2* d_rds_pair = nullptr;  // RDS low-pass taps per thread, two per entry (see k_rds_backend)
+    float* d_audio_tm = nullptr;   // thread-major audio taps of the phase-class resampler (k_audio_updown_pc), nullptr: not applicable
+    int* d_audio_res = nullptr;    // output residue per thread of that kernel
+    float* d_rds_perm = nullptr;   // permuted RDS low-pass taps
     int* d_rds_thread_phase = nullptr;
     // input
     uint8_t* d_iq[2] = {nullptr, nullptr};  // staging for process_host
@@ -228,7 +230,7 @@ cudaError_t copy_rows_h2d(sdrb_chain* c, uint8_t* dst, const uint8_t* h_iq, size
 size_t rds_backend_smem(int n_if, int n_out) {
     const int rrc_tiles = (n_out + kRrcTile - 1) / kRrcTile;
     const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;
-    return sizeof(float) * (2 * round_up((size_t)n_if + kState + 4, 2) + nfilt + nfilt / kRrcR + 8);
+    return sizeof(float) * (round_up((size_t)n_if + kState, 4) + nfilt + nfilt / kRrcR + 8);
 }
 
 // Makes the caller-visible stream wait for everything issued on the internal streams (no host blocking).
@@ -388,16 +390,25 @@ int process_block_impl(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cuda
         a.dc_pitch = c->sdc.pitch;
         a.n_in = n_if; a.n_out = c->info.audio_block; a.up = c->up; a.down = c->down;
         a.taps_pm = c->d_audio_pm;
+        a.taps_tm = c->d_audio_tm;
+        a.thread_res = c->d_audio_res;
         a.pcm = c->d_pcm[b & 1]; a.pcm_pitch = c->pcm_pitch;
         a.mono_out = keep ? c->d_mono : nullptr;
         a.dc_out = keep ? c->d_sfilt : nullptr;
         if (c->up == 1 && c->down == 5) rc = launch_audio_decim<5>(c, a, sb);
         else if (c->up == 1 && c->down == 9) rc = launch_audio_decim<9>(c, a, sb);
         else {
-            dim3 grid((a.n_out + 127) / 128, S);
-            if (c->stereo) k_audio_updown<true><<<grid, 128, 0, sb>>>(a);
-            else k_audio_updown<false><<<grid, 128, 0, sb>>>(a);
-            rc = check_launch(c, "k_audio_updown", sb);
+            if (c->d_audio_tm) {  // phase classes: one CTA per stream, the block staged whole in shared memory
+                const size_t smem = sizeof(float) * (size_t)(n_if + kState) * (c->stereo ? 2 : 1);
+                if (c->stereo) k_audio_updown_pc<true><<<S, kUpdThreads, smem, sb>>>(a);
+                else k_audio_updown_pc<false><<<S, kUpdThreads, smem, sb>>>(a);
+                rc = check_launch(c, "k_audio_updown_pc", sb);
+            } else {
+                dim3 grid((a.n_out + 127) / 128, S);
+                if (c->stereo) k_audio_updown<true><<<grid, 128, 0, sb>>>(a);
+                else k_audio_updown<false><<<grid, 128, 0, sb>>>(a);
+                rc = check_launch(c, "k_audio_updown", sb);
+            }
         }
         if (rc) return rc;
     }
@@ -406,7 +417,7 @@ int process_block_impl(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cuda
         RdsArgs a{};
         a.dc = c->rdc.cur(b); a.dc_pitch = c->rdc.pitch;
         a.n_in = n_if; a.n_out = c->info.rds_block; a.sps = 39; a.rds_on = c->cfg.rds_on;
-        a.taps_pair = c->d_rds_pair;
+        a.taps_perm = c->d_rds_perm;
         a.thread_phase = c->d_rds_thread_phase;
         a.rrc = c->rrc_h;
         a.filt_state_in = c->d_filt_state[b & 1];
@@ -606,6 +617,36 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
                 for (int j = 0; j < kTaps; j++) pm[(size_t)p * kTaps + j] = ah[p + c->up * j];
             TRY(dalloc(c, (void**)&c->d_audio_pm, pm.size() * sizeof(float)));
             TRYCU(cudaMemcpyAsync(c->d_audio_pm, pm.data(), pm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            // phase-class resampler (k_audio_updown_pc): applicable when every residue class has the same number of outputs
+            const int n_if_ = (1470 * c->down) / c->up, n_out_ = (int)(((long long)n_if_ * c->up) / c->down);
+            const size_t smem_pc = sizeof(float) * (size_t)(n_if_ + kState) * (c->stereo ? 2 : 1);
+            if (c->up <= kUpdThreads && n_out_ % c->up == 0 && n_out_ / c->up <= kUpdMaxQ && smem_pc <= 200 * 1024) {
+                // thread -> residue: a half-warp's loads (64-bit for stereo, 32-bit for mono: then a whole warp) hit distinct
+                // banks when the input offsets floor(r down / up) differ modulo 16 (32) among its lanes
+                const int group = c->stereo ? 16 : 32;
+                std::vector<int> res(kUpdThreads, -1), left;
+                std::vector<int> next(group);
+                for (int k = 0; k < group; k++) next[k] = k;
+                for (int r = 0; r < c->up; r++) {
+                    int& sl = next[(int)(((long long)r * c->down) / c->up) % group];
+                    if (sl < kUpdThreads) { res[sl] = r; sl += group; }
+                    else left.push_back(r);
+                }
+                for (int th = 0; th < kUpdThreads && !left.empty(); th++)
+                    if (res[th] < 0) { res[th] = left.back(); left.pop_back(); }
+                std::vector<float> tm((size_t)kTaps * kUpdThreads, 0.0f);
+                for (int th = 0; th < kUpdThreads; th++) {
+                    if (res[th] < 0) continue;
+                    const int phase = (int)(((long long)res[th] * c->down) % c->up);
+                    for (int j = 0; j < kTaps; j++) tm[(size_t)j * kUpdThreads + th] = ah[phase + c->up * j];
+                }
+                TRY(dalloc(c, (void**)&c->d_audio_tm, tm.size() * sizeof(float)));
+                TRY(dalloc(c, (void**)&c->d_audio_res, kUpdThreads * sizeof(int)));
+                TRYCU(cudaMemcpyAsync(c->d_audio_tm, tm.data(), tm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+                TRYCU(cudaMemcpyAsync(c->d_audio_res, res.data(), kUpdThreads * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+                TRYCU(cudaFuncSetAttribute(k_audio_updown_pc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pc));
+                TRYCU(cudaFuncSetAttribute(k_audio_updown_pc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pc));
+            }
             TRYCU(cudaStreamSynchronize(c->stream));
         }
     }
@@ -613,40 +654,24 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         const int nh = kTaps * kRdsUp;
         std::vector<float> lh(nh);
         TRY(sdrb_design_lpf_gain((float)(cfg->if_Fs * kRdsUp), 3e3f, nh, kRdsUp, lh.data()));  // src/rds.cpp:61
-        // thread -> output residue tp (outputs n = tp + 247 q).  A thread reads its input pairs with LDS.128 at pair index
-        // e0 - 2 i (+ 1280 per output pair), e0 = off0 + 2 - (off0 & 1), off0 = floor(640 tp / 247) + 100: a quarter-warp's
-        // eight 16-byte accesses are conflict free when (e0 / 2) mod 8 differs among its lanes, so residues are dealt to
-        // thread slots by that class (any left over take whatever slot is free).
+        // thread -> output residue: warp by warp, 32 residues whose input offsets floor(640 tp/247) differ modulo 32
         std::vector<int> thread_phase(256, -1);
         {
-            auto cls = [](int tp) { const int off0 = (kRdsDown * tp) / kRdsUp + kState; return ((off0 + 2 - (off0 & 1)) / 2) & 7; };
-            std::vector<int> left;
-            int next_slot[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-            for (int tp = 0; tp < kRdsUp; tp++) {
-                int& sl = next_slot[cls(tp)];
-                if (sl < 256) { thread_phase[sl] = tp; sl += 8; }
-                else left.push_back(tp);
-            }
-            for (int th = 0; th < 256 && !left.empty(); th++)
-                if (thread_phase[th] < 0) { thread_phase[th] = left.back(); left.pop_back(); }
+            std::vector<std::vector<int>> by_bank(32);
+            for (int tp = 0; tp < kRdsUp; tp++) by_bank[((kRdsDown * tp) / kRdsUp) % 32].push_back(tp);
+            for (int b = 0; b < 32; b++)
+                for (size_t i = 0; i < by_bank[b].size(); i++) thread_phase[32 * i + b] = by_bank[b][i];  // at most 8 per bank
         }
-        std::vector<float2> pair((size_t)kResGroups * 256, make_float2(0.0f, 0.0f));
+        std::vector<float> perm((size_t)kTaps * 256, 0.0f);
         for (int th = 0; th < 256; th++) {
             const int tp = thread_phase[th];
             if (tp < 0) continue;
             const int phase = (kRdsDown * tp) % kRdsUp;
-            const int par = ((kRdsDown * tp) / kRdsUp + kState) & 1;
-            for (int i = 0; i < kResGroups; i++) {
-                const int jb = 2 * i + par, ja = jb - 1;  // taps of group i, MAC order ja then jb; out of range = zero tap
-                float2 h2 = make_float2(0.0f, 0.0f);
-                if (ja >= 0 && ja < kTaps) h2.x = lh[phase + kRdsUp * ja];
-                if (jb >= 0 && jb < kTaps) h2.y = lh[phase + kRdsUp * jb];
-                pair[(size_t)i * 256 + th] = h2;
-            }
+            for (int j = 0; j < kTaps; j++) perm[(size_t)j * 256 + th] = lh[phase + kRdsUp * j];
         }
-        TRY(dalloc(c, (void**)&c->d_rds_pair, pair.size() * sizeof(float2)));
+        TRY(dalloc(c, (void**)&c->d_rds_perm, perm.size() * sizeof(float)));
         TRY(dalloc(c, (void**)&c->d_rds_thread_phase, 256 * sizeof(int)));
-        TRYCU(cudaMemcpyAsync(c->d_rds_pair, pair.data(), pair.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+        TRYCU(cudaMemcpyAsync(c->d_rds_perm, perm.data(), perm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         TRYCU(cudaMemcpyAsync(c->d_rds_thread_phase, thread_phase.data(), 256 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         TRYCU(cudaStreamSynchronize(c->stream));
     }

@@ -790,6 +790,9 @@ struct AudioArgs {
     int n_out;            // audio frames per block
     int up, down;
     const float* taps_pm; // generic path: phase-major taps [up][kTaps] (taps_pm[p*kTaps+j] = h[p + up*j])
+    // phase-class path (k_audio_updown_pc): thread-major taps [kTaps][kUpdThreads] and the output residue each thread owns
+    const float* taps_tm;
+    const int* thread_res;
     int16_t* pcm;         // [n_streams][pcm_pitch]
     size_t pcm_pitch;
     float* mono_out;      // optional [n_streams][n_out]
@@ -881,6 +884,86 @@ __global__ void __launch_bounds__(128) k_audio_updown(const AudioArgs a) {
     }
 }
 
+// Rational resampler by phase classes (147/800 and 147/1280 of modes 2 and 3; any up <= kUpdThreads that divides n_out).
+// Outputs n and n + up use the same polyphase branch h[phase + up j] and inputs `down` apart, so one thread owns the
+// residue class n = r + up q, q = 0 .. n_out/up - 1 (10 outputs here), streams its 101 branch taps once (thread-major
+// table: a warp's tap loads are one coalesced row) and reads its inputs from the block staged whole in shared memory.
+// Stereo: the staged element is (mono, stereo_dc), so one 64-bit load feeds both lanes of a packed MAC; mono: outputs
+// q and q+1 share the packed accumulator.  Which residue a thread owns is a host-made permutation that spreads a
+// half-warp's loads over the banks.  (The one-thread-per-output kernel above did 101 scattered tap loads and 101-202
+// global input loads per output: 0.23 ms per 1024 mode-2 blocks, 4 % of the MAC issue rate.)
+constexpr int kUpdThreads = 160;
+constexpr int kUpdMaxQ = 10;
+
+template <bool STEREO>
+__global__ void __launch_bounds__(kUpdThreads) k_audio_updown_pc(const AudioArgs a) {
+    extern __shared__ __align__(16) float upd_smem[];
+    const int s = blockIdx.x, t = threadIdx.x;
+    const int nx = a.n_in + kState;
+    const float* mx = a.mono_x + (size_t)s * a.mono_pitch - kState;
+    if (STEREO) {
+        float2* sx = reinterpret_cast<float2*>(upd_smem);
+        const float* dx = a.dc_x + (size_t)s * a.dc_pitch - kState;
+        for (int u = t; u < nx; u += kUpdThreads) sx[u] = make_float2(__fadd_rn(0.0f, mx[u]), dx[u]);  // 0.0f + x: src/stereo.cpp:88
+    } else {
+        for (int u = t; u < nx; u += kUpdThreads) upd_smem[u] = mx[u];
+    }
+    __syncthreads();
+    const int r = a.thread_res[t];
+    if (r < 0) return;
+    const int Q = a.n_out / a.up;
+    const long long rd = (long long)r * a.down;
+    const int base = (int)(rd / a.up) + kState;  // index of x[(n*down - phase)/up] for q = 0
+    if (STEREO) {
+        const float2* xb = reinterpret_cast<const float2*>(upd_smem) + base;
+        float2 acc[kUpdMaxQ];
+#pragma unroll
+        for (int q = 0; q < kUpdMaxQ; q++) acc[q] = make_float2(0.0f, 0.0f);
+#pragma unroll 4
+        for (int j = 0; j < kTaps; j++) {
+            const float hj = __ldg(a.taps_tm + j * kUpdThreads + t);
+#pragma unroll
+            for (int q = 0; q < kUpdMaxQ; q++)
+                if (q < Q) acc[q] = mac(acc[q], hj, xb[q * a.down - j]);
+        }
+#pragma unroll
+        for (int q = 0; q < kUpdMaxQ; q++) {
+            if (q >= Q) break;
+            const int n = r + a.up * q;
+            int16_t* p = a.pcm + (size_t)s * a.pcm_pitch + 2 * n;
+            p[0] = to_pcm(__fmul_rn(16384.0f, __fadd_rn(acc[q].x, acc[q].y)));
+            p[1] = to_pcm(__fmul_rn(16384.0f, __fadd_rn(acc[q].x, -acc[q].y)));
+            if (a.mono_out) {
+                a.mono_out[(size_t)s * a.n_out + n] = acc[q].x;
+                a.dc_out[(size_t)s * a.n_out + n] = acc[q].y;
+            }
+        }
+    } else {
+        const float* xb = upd_smem + base;
+        float2 acc[kUpdMaxQ / 2];
+#pragma unroll
+        for (int q = 0; q < kUpdMaxQ / 2; q++) acc[q] = make_float2(0.0f, 0.0f);
+#pragma unroll 4
+        for (int j = 0; j < kTaps; j++) {
+            const float hj = __ldg(a.taps_tm + j * kUpdThreads + t);
+#pragma unroll
+            for (int q = 0; q < kUpdMaxQ / 2; q++) {
+                const float x0 = 2 * q < Q ? xb[2 * q * a.down - j] : 0.0f;
+                const float x1 = 2 * q + 1 < Q ? xb[(2 * q + 1) * a.down - j] : 0.0f;
+                acc[q] = mac(acc[q], hj, make_float2(x0, x1));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kUpdMaxQ; q++) {
+            if (q >= Q) break;
+            const int n = r + a.up * q;
+            const float y = (q & 1) ? acc[q / 2].y : acc[q / 2].x;
+            a.pcm[(size_t)s * a.pcm_pitch + n] = to_pcm(__fmul_rn(16384.0f, y));
+            if (a.mono_out) a.mono_out[(size_t)s * a.n_out + n] = y;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5  RDS back end, one CTA per stream: 247/640 resampler + 3 kHz LPF, RRC, clock recovery, slicer,
 // Manchester and differential decode, and (every 15 decode blocks) frame sync.
@@ -918,7 +1001,7 @@ struct RdsArgs {
     int n_out;             // n_in*247/640
     int sps;
     int rds_on;
-    const float2* taps_pair; // [kResGroups][256]: the thread's polyphase branch h_lpf[phase + 247 j], two taps per entry, see k_rds_backend
+    const float* taps_perm;  // [kTaps][256]: taps_perm[j*256 + thread] = h_lpf[(640*tp % 247) + 247*j], tp = thread_phase[thread]
     const int* thread_phase; // [256]: the output residue tp (n = tp mod 247) each thread owns, -1 = idle
     Taps101 rrc;
     float* filt_state_in;    // [n_streams][kState] last rds_filt samples of the previous block
@@ -957,7 +1040,7 @@ __device__ __forceinline__ uint32_t bitbuf_window26(const uint32_t* buf, int idx
 constexpr int kRrcR = 12;
 constexpr int kRrcTile = kRrcR * kRdsThreads;  // 3072 outputs per pass
 constexpr int kResQ = 12;                      // resampler outputs per thread: ceil(2836 / 247); the kernel requires n_out <= 12 * 247
-constexpr int kResGroups = 51;                 // tap groups (two taps each) per polyphase branch
+
 
 __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_constant__ RdsArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -966,8 +1049,8 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     const int n_in = a.n_in, n_out = a.n_out;
     const int rrc_tiles = (n_out + kRrcTile - 1) / kRrcTile;
     const int nfilt_pad = rrc_tiles * kRrcTile + kState;
-    float2* sP = reinterpret_cast<float2*>(smem);        // [n_in + kState + 4] input pairs; later reused as sclean [n_out]
-    float* sfilt = smem + 2 * ((n_in + kState + 4 + 1) / 2 * 2);  // padded layout, pad_pos<kRrcR>
+    float* sdc = smem;                                // [n_in + kState]; later reused as sclean [n_out]
+    float* sfilt = smem + (n_in + kState + 3) / 4 * 4;  // padded layout, pad_pos<kRrcR>
     __shared__ int ssum[64];
     __shared__ int ssym[160];
     __shared__ int8_t stype[kBitBufWords * 32];
@@ -981,21 +1064,9 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     const int start_in = st->start, half_in = st->half_symbol, last_in = st->last_bit;
     const int nbits_in = st->nbits, decoder_cont_in = st->decoder_cont;
 
-    // ---- stage rds_dc (with the carried 100-sample state in front) as PAIRS: sP[u + 2] = (x[u], x[u + 640]).
-    // Outputs n and n + 247 of the resampler read inputs 640 apart, so one 64-bit word feeds both lanes of a packed MAC and
-    // one LDS.128 (two consecutive u) feeds two taps of two outputs.  Two zero entries in front and behind: the zero taps
-    // that pad a thread's branch to whole groups (below) multiply them.
-    const int nx = n_in + kState;
-    {
-        const float* dc = a.dc + (size_t)s * a.dc_pitch - kState;
-        for (int u = t; u < nx; u += kRdsThreads) {
-            const float x = dc[u];
-            sP[u + 2].x = x;
-            if (u >= kRdsDown) sP[u - kRdsDown + 2].y = x;
-        }
-    }
-    for (int u = nx - kRdsDown + t; u < nx + 2; u += kRdsThreads) sP[u + 2].y = 0.0f;  // partners beyond the block
-    if (t < 2) { sP[t] = make_float2(0.0f, 0.0f); sP[nx + 2 + t].x = 0.0f; }
+    // ---- stage rds_dc (with the carried 100-sample state in front)
+    const float* dc = a.dc + (size_t)s * a.dc_pitch - kState;
+    for (int u = t; u < n_in + kState; u += kRdsThreads) sdc[u] = dc[u];
     for (int u = t; u < kState; u += kRdsThreads)
         sfilt[pad_pos<kRrcR>(u)] = a.filt_state_in[(size_t)s * kState + u];
     for (int u = n_out + kState + t; u < nfilt_pad; u += kRdsThreads) sfilt[pad_pos<kRrcR>(u)] = 0.0f;
@@ -1004,31 +1075,25 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
 
     // ---- 247/640 resampler (/root/reference/src/filter.cpp:123-147, src/rds.cpp:130).
     // Outputs n and n+247 share the polyphase branch, so one thread owns n = tp + 247 q, q = 0..11, and streams its 101
-    // branch taps h[phase + 247 j] once; outputs 2p and 2p+1 form one packed accumulator (their inputs are the two halves of
-    // a pair, see above).  Taps come two at a time (j_a, j_b = j_a + 1, MAC order j_a then j_b = the reference's ascending
-    // k), with j_b of the same parity as the thread's input offset so that the pair address off - j_b is 16-byte aligned for
-    // LDS.128; the branch is zero-padded to 51 such groups by the host (a zero tap adds +-0 to the accumulator: no effect).
-    // Which tp a thread owns is a host-made permutation (thread_phase) that spreads each quarter-warp's 16-byte accesses over
-    // all eight 16-byte bank groups.
+    // branch taps h[phase + 247 j] once; outputs 2p and 2p+1 share one packed accumulator (FFMA2 + FADD2: half the
+    // floating-point instructions of the scalar form, so the one shared-memory load per MAC has issue slots to go into).
+    // Which tp a thread owns is a host-made permutation (thread_phase): the 32 lanes of a warp get input offsets
+    // floor(640 tp / 247) that are distinct modulo 32, so those loads are bank-conflict free.
     const int tp = a.thread_phase[t];
     if (tp >= 0) {
-        const int off0 = (kRdsDown * tp) / kRdsUp + kState;  // index of x[(n*down - phase)/up] for q = 0
-        const float2* pbase = sP + 2 + off0 - ((off0 & 1) ? 1 : 0);  // &pair(off0 - j_b) for group 0 (j_b = 0 or 1)
+        const float* xb = sdc + (kRdsDown * tp) / kRdsUp + kState;  // x[(n*down - phase)/up] for q = 0
         float2 acc[kResQ / 2];
 #pragma unroll
         for (int pq = 0; pq < kResQ / 2; pq++) acc[pq] = make_float2(0.0f, 0.0f);
-#ifndef SDRB_RES_UNROLL
-#define SDRB_RES_UNROLL 17
-#endif
-        constexpr int kResUnroll = SDRB_RES_UNROLL;  // tap loads in flight ahead of their MACs
-#pragma unroll kResUnroll
-        for (int i = 0; i < kResGroups; i++) {
-            const float2 h = __ldg(a.taps_pair + i * 256 + t);
+        const bool last_valid = (kResQ - 1) * kRdsUp + tp < n_out;  // output 11 exists for tp < 119 only: its inputs must not be read beyond the block
+#pragma unroll 8  // eight tap loads in flight ahead of their MACs
+        for (int j = 0; j < kTaps; j++) {
+            const float hj = __ldg(a.taps_perm + j * 256 + t);
 #pragma unroll
             for (int pq = 0; pq < kResQ / 2; pq++) {
-                const float4 v = *reinterpret_cast<const float4*>(pbase + 2 * kRdsDown * pq - 2 * i);  // pair(u), pair(u+1)
-                acc[pq] = mac(acc[pq], h.x, make_float2(v.z, v.w));  // tap j_a on x[off - j_a] = pair(u + 1)
-                acc[pq] = mac(acc[pq], h.y, make_float2(v.x, v.y));  // tap j_b on x[off - j_b] = pair(u)
+                const float x0 = xb[2 * kRdsDown * pq - j];
+                const float x1 = (pq == kResQ / 2 - 1 && !last_valid) ? 0.0f : xb[2 * kRdsDown * pq + kRdsDown - j];
+                acc[pq] = mac(acc[pq], hj, make_float2(x0, x1));
             }
         }
 #pragma unroll
