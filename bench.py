@@ -452,6 +452,7 @@ def main():
     stream = torch.cuda.current_stream()
     ch.set_stream(stream.cuda_stream)
     ch.set_overlap(True)
+    part = ch.sm_partition()  # (PLL SMs, FIR SMs) of the green-context split, (0, 0) if the driver refused it
     shard = load_mod("sdrb_shard", "real-time-sdr_b200/shard.py")
     mine = shard.station_range(rank, world, world * S)  # weak scaling: S stations per rank
     inputs = build_inputs(torch, gen, S, bb, pitch, dev, first_station=mine.start)
@@ -659,7 +660,7 @@ def main():
         line = {"metric": metric_name(), "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": config_dict(S, bp, pitch),
+                "config": dict(config_dict(S, bp, pitch), sm_partition={"pll_sms": part[0], "fir_sms": part[1]}),
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "sustained": sustained, "host": {"numa_binding_rank0": numa, "cpus": os.cpu_count()}}
         emit(line)

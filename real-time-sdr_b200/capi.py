@@ -28,7 +28,7 @@ EXPORTS = [
     "sdrb_pinned_free", "sdrb_chain_set_stream", "sdrb_chain_join", "sdrb_chain_read_results",
     "sdrb_manchester_decode", "sdrb_differential_decode", "sdrb_frame_sync",
     "sdrb_chain_state_load_n", "sdrb_chain_input_consumed", "sdrb_chain_rds_overflows",
-    "sdrb_chain_pll_redos", "sdrb_chain_pll_redo_detail", "sdrb_chain_check_guards",
+    "sdrb_chain_pll_redos", "sdrb_chain_pll_redo_detail", "sdrb_chain_check_guards", "sdrb_chain_sm_partition",
     "sdrb_chain_state_item_offset", "sdrb_rds_sync",
 ]
 
@@ -129,6 +129,7 @@ def load(path: str | None = None) -> C.CDLL:
     L.sdrb_chain_rds_overflows.argtypes = [vp, C.POINTER(C.c_uint * 3)]
     L.sdrb_chain_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(cf), ci, C.POINTER(ci)]
     L.sdrb_chain_set_profiling.argtypes = [vp, ci]
+    L.sdrb_chain_sm_partition.argtypes = [vp, C.POINTER(C.c_int * 2)]
     L.sdrb_chain_launch_count.argtypes = [vp]
     L.sdrb_chain_launch_count.restype = C.c_longlong
     L.sdrb_chain_set_overlap.argtypes = [vp, ci]
@@ -327,6 +328,12 @@ class Chain:
 
     def launch_count(self) -> int:
         return int(self.L.sdrb_chain_launch_count(self.h))
+
+    def sm_partition(self) -> tuple:
+        """(SMs owned by the PLL stream, SMs owned by the FIR streams); (0, 0): no partition (plain priority streams)."""
+        c = (C.c_int * 2)()
+        check(self.L.sdrb_chain_sm_partition(self.h, C.byref(c)))
+        return int(c[0]), int(c[1])
 
 
 class RdsTextDecoder:

@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#define SDRB_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #if defined(__CUDACC__)
 #define SDRB_HD __host__ __device__ __forceinline__
 #else
@@ -495,6 +496,7 @@ struct PllFast {
     bool generic_next;  // sa/cr/r/kq are not valid (fbI/fbQ are): use the general atan2 at the next step
     double magic;       // 1.5 * 2^(E+29), E = binade of the current NCO phase: td + magic - magic rounds td to float precision
     uint32_t rmin_hi;   // high word of the smallest |r| the speculative step accepts in that binade (reduce_rmin, rounded up)
+    uint32_t texp;      // exponent field (high word, bits 20-30) of that binade: what the unrounded phase td must show
 };
 SDRB_HD uint32_t dhi(double v) {
 #if defined(__CUDA_ARCH__)
@@ -623,6 +625,7 @@ SDRB_HD void pll_fast_sincos(float trigArg, PllFast& f) {
     double x = (double)trigArg;
     f.magic = float_round_magic(x);
     f.rmin_hi = reduce_rmin_hi(x);
+    f.texp = dhi(x) & 0x7FF00000u;
     bool ok = fabs(x) < kReduceLimit && fabs(x) > 0x1p-100;
     if (ok) {
         double sa, cr_, r;
@@ -813,6 +816,81 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
     return (float)td;
 }
 
+// ---- the speculative step cut in two, for the rotated loop of the batched kernel ----
+// head: the phase detector of one sample (everything up to e, the double whose float rounding is errorD); a pure function
+//       of the loop state and the input, so it can be evaluated for the NEXT chunk's first sample before the current
+//       chunk's acceptance flag is looked at: the branch on that flag then resolves in the shadow of the head instead of
+//       stopping the recurrence (the flag's last inputs, the float-tie tests of sa / cr, are ready ~45 cycles before it).
+// tail: loop filter, NCO phase, reduction and the sine / cosine kernels (e -> new sa, cr, r, kq).
+// The tests are leaner than pll_step_spec's (same guarantees, fewer instructions beside the chain):
+//   e   : RN_f(e - 2^-43) == RN_f(e + 2^-43), i.e. no float rounding step within the error bound of e, whatever its
+//         binade; replaces the exponent-dependent window of ambig_abs (and rejects |e| < ~2^-19 by itself);
+//   sa,cr : low 29 bits within 256 of the tie pattern, as one add and one masked compare;
+//   td  : exponent field against the one stored with the magic constant (one masked compare);
+//   in  : the range test is made once per chunk on min / max of the four inputs (pll_chunk4r).
+struct PllHead {
+    double e;
+    uint32_t Ke, bh;  // bh: high word of base (for the +-2 test)
+};
+constexpr double kAtanTol = 0x1p-43;  // 2^kAtanTolLog2
+SDRB_HD unsigned ambig_tie29(double v) {  // low 29 bits in [tie - 256, tie + 255]
+    return (unsigned)((((dlo(v) + kAmbigUlps) & 0x1FFFFE00u) ^ 0x10000000u) == 0u);
+}
+SDRB_HD PllHead pll_spec_head(float in, double rin, const PllFast& f, const PllK& kk) {
+    const uint32_t rhi = dhi(f.r);
+    const uint32_t rs = rhi & 0x80000000u;  // r < 0
+    const unsigned m = ((unsigned)f.kq + ((fbits(in) >> 31) << 1)) & 3u;
+    const uint32_t mmhi = (m & 1u) ? ((m & 2u) ? 0x3FF00000u : 0xBFF00000u) : ((m & 2u) ? (0x40000000u ^ rs) : 0u);  // see pll_step_spec
+    const double mm = mkd(mmhi, 0u);
+    const double ars = mkd(dhi(rin) ^ rs, dlo(rin));  // (-1)^[r<0] / |in|
+    // -- the chain: sa, cr -> float -> products -> double -> e --
+    const float fa = bitsf(d2f_known(f.sa, 0xC0000000u));
+    const double mc = dmul(f.cr, -ars);
+    const float fc = bitsf(d2f_known(f.cr, 0xC0000000u));
+    const double ma = dmul(f.sa, ars);
+    const float pa = fmul(fabsf(in), fa), pc = fmul(fabsf(in), fc);
+    const double base = dfma(mm, kk.v[kKPio2M], dfma(mm, kk.v[kKPio2H], -f.r));
+    const uint32_t bh = dhi(base);
+    const uint32_t Ke = d2f_K(bh);
+    const double e = dfma(f2d_pos(pc), ma, dfma(f2d_pos(pa), mc, base));
+    return PllHead{e, Ke, bh};
+}
+// The tests of a head: sa / cr are the values it was computed from (their float roundings fa, fc must not be near a tie);
+// wrap (|e| < pi; NaN / inf from an unusable input land here too), float rounding of e, base at +-2.
+SDRB_HD void pll_spec_head_tests(const PllHead& h, double sa, double cr_, unsigned& bad) {
+    const uint32_t elo = d2f_known(dadd(h.e, -kAtanTol), h.Ke), ehi = d2f_known(dadd(h.e, kAtanTol), h.Ke);
+    bad |= SDRB_BAD((dhi(h.e) & 0x7FFFFFFFu) >= 0x400921F9u, 1) | SDRB_BAD(elo != ehi, 2) |
+           SDRB_BAD(((h.bh & 0x7FFFFFFFu) - 0x3FFFFFFFu) <= 1u, 3) | SDRB_BAD(ambig_tie29(sa), 6) | SDRB_BAD(ambig_tie29(cr_), 7);
+}
+SDRB_HD float pll_spec_tail(const PllHead& h, PllFast& f, const PllCoef& k, const PllK& kk, unsigned& bad) {
+    const float errorD = bitsf(d2f_known(h.e, h.Ke));
+    f.integ = fadd(f.integ, fmul(k.Ki, errorD));
+    f.phase = fadd(fadd(f.phase, fmul(k.Kp, errorD)), f.integ);
+    f.trigOffset = dadd(f.trigOffset, 1.0);
+    const double phd = (double)f.phase;
+    const double td = dadd(dmul(k.w, f.trigOffset), phd);
+    const double xd = dadd(dadd(td, f.magic), -f.magic);  // (double)(float)td, see pll_step_spec
+    const double tm = dfma(xd, kk.v[kK2OverPi], kMagicRint);
+    const double kd = dadd(tm, -kMagicRint);
+    const int q = (int)dlo(tm) & 3;
+    const double r = dfma(-kd, kk.v[kKPio2M], dfma(-kd, kk.v[kKPio2H], xd));
+    const uint32_t rah = dhi(r) & 0x7FFFFFFFu;
+    double sa, cr_;
+    sincos_poly2k(r, mkd(rah, dlo(r)), sa, cr_, kk);
+    // td left the binade of the magic constant; r tiny.  (sa / cr near a float tie: tested by the head that uses them.)
+    bad |= SDRB_BAD(((dhi(td) & 0x7FF00000u) ^ f.texp) != 0u, 4) | SDRB_BAD(rah < f.rmin_hi, 5);
+    f.sa = sa;
+    f.cr = cr_;
+    f.r = r;
+    f.kq = q;
+    return (float)td;
+}
+// The loop state as the careful path needs it: the speculative steps leave sa / cr without a tie test and fbI / fbQ behind,
+// so everything is derived again from the float NCO phase (/root/reference/src/pll.cpp:47 with the current values).
+SDRB_HD void pll_fast_resync(PllFast& f, const PllCoef& k) {
+    pll_fast_sincos((float)dadd(dmul(k.w, f.trigOffset), (double)f.phase), f);
+}
+
 #if defined(__CUDA_ARCH__)
 #define SDRB_RARE __device__ __noinline__
 #else
@@ -821,6 +899,7 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
 // the careful repeat of four steps (rare: kept out of line on the device so the hot loop stays small)
 SDRB_RARE void pll_redo4(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, PllFast& f,
                          const PllCoef& k, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3) {
+    if (!f.generic_next) pll_fast_resync(f, k);  // sa / cr may be untested (rotated loop): derive the state again from the float phase
     t0 = pll_step_fast(i0, pll_guard_recip(i0, r0), f, k, tab);  // r0..r3 are raw reciprocals: guarded here
     t1 = pll_step_fast(i1, pll_guard_recip(i1, r1), f, k, tab);
     t2 = pll_step_fast(i2, pll_guard_recip(i2, r2), f, k, tab);
@@ -855,6 +934,54 @@ SDRB_HD void pll_chunk4(float i0, float i1, float i2, float i3, double r0, doubl
         f = again;
         t0 = a0; t1 = a1; t2 = a2; t3 = a3;
     }
+}
+
+
+// The rotated chunk: `h` is the head of this chunk's first sample, computed by the previous call (pll_chunk4r_prime before
+// the first) and tested here; n0 / rn0 are the next chunk's first sample and its raw reciprocal (anything if there is none:
+// the head is a pure function and its result is then never used).  `first` (0/1): the state did not come out of a
+// speculative step (start of a block, after a careful repeat) and says generic_next.
+SDRB_HD void pll_chunk4r_prime(float i0, double r0, const PllFast& f, const PllK& kk, PllHead& h) { h = pll_spec_head(i0, r0, f, kk); }
+SDRB_HD void pll_chunk4r(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, float n0, double rn0,
+                         PllFast& f, PllHead& h, const PllCoef& k, const PllK& kk, const AtanTab& tab, float& t0, float& t1,
+                         float& t2, float& t3, unsigned long long* redo_ctr = nullptr) {
+    const PllFast saved = f;
+    unsigned bad = SDRB_BAD(f.generic_next, 8);
+    // every |in| of the chunk within [2^-90, 2^90): min / max instead of four tests (a NaN input is dropped by fmin / fmax
+    // and shows up as a NaN e, which the wrap test rejects; zero and subnormal inputs have an infinite reciprocal: same)
+    const float mn = fminf(fminf(fabsf(i0), fabsf(i1)), fminf(fabsf(i2), fabsf(i3)));
+    const float mx = fmaxf(fmaxf(fabsf(i0), fabsf(i1)), fmaxf(fabsf(i2), fabsf(i3)));
+    bad |= SDRB_BAD(!(mn >= 0x1p-90f), 0) | SDRB_BAD(!(mx < 0x1p90f), 0);
+    pll_spec_head_tests(h, saved.sa, saved.cr, bad);
+    t0 = pll_spec_tail(h, f, k, kk, bad);
+    PllHead g = pll_spec_head(i1, r1, f, kk);
+    pll_spec_head_tests(g, f.sa, f.cr, bad);
+    t1 = pll_spec_tail(g, f, k, kk, bad);
+    g = pll_spec_head(i2, r2, f, kk);
+    pll_spec_head_tests(g, f.sa, f.cr, bad);
+    t2 = pll_spec_tail(g, f, k, kk, bad);
+    g = pll_spec_head(i3, r3, f, kk);
+    pll_spec_head_tests(g, f.sa, f.cr, bad);
+    t3 = pll_spec_tail(g, f, k, kk, bad);
+    PllHead hn = pll_spec_head(n0, rn0, f, kk);  // tested by the next call
+    if (SDRB_UNLIKELY(bad != 0u)) {
+#if defined(__CUDA_ARCH__)
+        if (redo_ctr) atomicAdd(redo_ctr, 1ull);
+#if defined(SDRB_PLL_DIAG)
+        for (int b = 0; b < 9; b++)
+            if ((bad >> b) & 1u) atomicAdd(redo_ctr + 2 * (1 + b), 1ull);
+#endif
+#else
+        if (redo_ctr) ++*redo_ctr;
+#endif
+        PllFast again = saved;
+        float a0, a1, a2, a3;
+        pll_redo4(i0, i1, i2, i3, r0, r1, r2, r3, again, k, tab, a0, a1, a2, a3);
+        f = again;
+        t0 = a0; t1 = a1; t2 = a2; t3 = a3;
+        hn = pll_spec_head(n0, rn0, f, kk);
+    }
+    h = hn;
 }
 
 }  // namespace cr

@@ -5,6 +5,7 @@
 // three thread bodies do per block (/root/reference/src/rffrontend.cpp:45-76, src/mono.cpp:29-49,
 // src/stereo.cpp:69-114, src/rds.cpp:95-192).  There is no CPU fallback: without a usable GPU every
 // entry point that needs one fails with SDRB_ERR_NO_DEVICE / SDRB_ERR_CUDA.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -86,6 +87,10 @@ struct sdrb_chain {
     // overlap mode: front end of block b+1 concurrent with PLL / back end of block b (see process_block)
     cudaStream_t s_front = nullptr, s_pll = nullptr, s_back = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in = nullptr, ev_front[kNRing] = {}, ev_pll[kNRing] = {}, ev_back[kNRing] = {}, ev_h2d[2] = {}, ev_consumed[2] = {}, ev_join = nullptr;
+    // SM partition (green contexts): the PLL stream owns pll_sms SMs, the FIR streams the rest; 0/0 when not in use
+    void* gctx_pll = nullptr;
+    void* gctx_fir = nullptr;
+    int part_pll_sms = 0, part_fir_sms = 0;
     bool input_is_host = false;  // the block being issued comes from process_host (its input is consumed by the H2D copy)
     bool pending = false;  // work issued on the internal streams that the main stream has not been joined with
     // taps
@@ -125,6 +130,80 @@ struct sdrb_chain {
 };
 
 namespace {
+
+// ---- SM partition -------------------------------------------------------------------------------------------------
+// k_pll is one dependent chain per sample: its warps must never wait for an SM or share one.  Stream priority plus a
+// whole-SM shared-memory reservation (round 1) keeps FIR CTAs off the SMs a running PLL kernel holds, but not off the
+// SMs it frees between two launches: the next launch then waits until those CTAs have drained (measured 0.03-0.11 ms per
+// step, profiles/README.md).  Green contexts (driver API, CUDA 12.4+) split the device for good: the PLL stream is
+// created in a context that owns `pll_sms` SMs, the front- and back-end streams in one that owns the rest.  The driver
+// entry points are looked up at run time (no link-time dependency on libcuda: the library must load on a CPU-only box);
+// if anything is missing or refused the chain keeps its ordinary priority streams.
+struct GreenApi {
+    CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+    CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+    CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+    CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+    CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+    CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+    bool ok = false;
+};
+const GreenApi& green_api() {
+    static GreenApi api = [] {
+        GreenApi a;
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+        };
+        a.ok = get("cuDeviceGet", (void**)&a.DeviceGet) && get("cuDeviceGetDevResource", (void**)&a.DeviceGetDevResource) &&
+               get("cuDevSmResourceSplitByCount", (void**)&a.DevSmResourceSplitByCount) &&
+               get("cuDevResourceGenerateDesc", (void**)&a.DevResourceGenerateDesc) && get("cuGreenCtxCreate", (void**)&a.GreenCtxCreate) &&
+               get("cuGreenCtxDestroy", (void**)&a.GreenCtxDestroy) && get("cuGreenCtxStreamCreate", (void**)&a.GreenCtxStreamCreate);
+        return a;
+    }();
+    return api;
+}
+// Creates the two contexts and the three compute streams in them; false (nothing created, nothing leaked) if unavailable.
+bool make_sm_partition(sdrb_chain* c, int pll_sms, int prio_lo, int prio_hi) {
+    const GreenApi& g = green_api();
+    if (!g.ok) return false;
+    CUdevice dev;
+    CUdevResource all, grp, rest;
+    unsigned int ngrp = 1;
+    if (g.DeviceGet(&dev, c->cfg.device) != CUDA_SUCCESS) return false;
+    if (g.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    if ((int)all.sm.smCount < pll_sms + 8) return false;
+    if (g.DevSmResourceSplitByCount(&grp, &ngrp, &all, &rest, 0, (unsigned)pll_sms) != CUDA_SUCCESS || ngrp != 1) return false;
+    if (grp.sm.smCount < (unsigned)pll_sms || rest.sm.smCount == 0) return false;
+    CUdevResourceDesc d_pll, d_fir;
+    if (g.DevResourceGenerateDesc(&d_pll, &grp, 1) != CUDA_SUCCESS || g.DevResourceGenerateDesc(&d_fir, &rest, 1) != CUDA_SUCCESS) return false;
+    CUgreenCtx gp = nullptr, gf = nullptr;
+    if (g.GreenCtxCreate(&gp, d_pll, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (g.GreenCtxCreate(&gf, d_fir, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) {
+        g.GreenCtxDestroy(gp);
+        return false;
+    }
+    CUstream sp = nullptr, sf = nullptr, sb = nullptr;
+    const bool ok = g.GreenCtxStreamCreate(&sp, gp, CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS &&
+                    g.GreenCtxStreamCreate(&sf, gf, CU_STREAM_NON_BLOCKING, prio_lo) == CUDA_SUCCESS &&
+                    g.GreenCtxStreamCreate(&sb, gf, CU_STREAM_NON_BLOCKING, prio_lo) == CUDA_SUCCESS;
+    if (!ok) {
+        for (CUstream st : {sp, sf, sb})
+            if (st) cudaStreamDestroy((cudaStream_t)st);
+        g.GreenCtxDestroy(gp);
+        g.GreenCtxDestroy(gf);
+        return false;
+    }
+    c->s_pll = (cudaStream_t)sp;
+    c->s_front = (cudaStream_t)sf;
+    c->s_back = (cudaStream_t)sb;
+    c->gctx_pll = gp;
+    c->gctx_fir = gf;
+    c->part_pll_sms = (int)grp.sm.smCount;
+    c->part_fir_sms = (int)rest.sm.smCount;
+    return true;
+}
 
 // Guard mode (environment variable SDRB_GUARD=1 at chain creation; a debugging aid, compute-sanitizer being unavailable
 // on the GPU pool): every allocation gets a canary zone on both sides, sdrb_chain_check_guards() verifies them.
@@ -497,6 +576,8 @@ int sdrb_chain_destroy(sdrb_chain* c) {
             cudaEventDestroy(t.e1[i]);
         }
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
+    for (void* g : {c->gctx_pll, c->gctx_fir})
+        if (g) green_api().GreenCtxDestroy((CUgreenCtx)g);
     delete c;
     return SDRB_OK;
 }
@@ -525,12 +606,13 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
     sdrb_chain* c = new sdrb_chain();
     c->cfg = *cfg;
     c->S = cfg->n_streams;
-    // SMs given to k_pll (measured, profiles/pll_sm_sweep_r1g.txt): one warp per SM on up to 64 SMs while the stations
-    // fit that way (<= 1024 stereo+RDS stations); beyond that the FIR kernels are the longer side of the step and get
-    // the SMs instead (32 for the PLL, more warps per CTA).
+    // SMs given to k_pll: 32 (two warps per SM at 1024 stereo+RDS stations).  Round 1 used 64 (one warp per SM) up to 1024
+    // stations; with the rotated PLL loop of round 2 the FIR kernels on the remaining 84 SMs had become the longer side of
+    // the step (profiles/README.md: 1.058 -> 0.979 ms per step at 1024 stations with 32; the PLL alone loses 1 %).
     {
         const int loops = cfg->type == 'r' ? 2 : 1;
-        c->pll_max_ctas = ((cfg->n_streams + 31) / 32 * loops <= kPllMaxCtas) ? kPllMaxCtas : kPllMaxCtas / 2;
+        (void)loops;
+        c->pll_max_ctas = kPllMaxCtas / 2;
     }
     if (const char* e = getenv("SDRB_PLL_MAX_CTAS")) {
         const int v = atoi(e);
@@ -582,9 +664,14 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         // its stream gets the highest priority so the block scheduler stops refilling SMs with FIR CTAs while PLL CTAs wait.
         int prio_lo = 0, prio_hi = 0;
         TRYCU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        for (cudaStream_t* st : {&c->s_front, &c->s_back, &c->s_h2d, &c->s_d2h})
-            TRYCU(cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio_lo));
-        TRYCU(cudaStreamCreateWithPriority(&c->s_pll, cudaStreamNonBlocking, prio_hi));
+        for (cudaStream_t* st : {&c->s_h2d, &c->s_d2h}) TRYCU(cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio_lo));
+        // SM partition for the overlap-mode streams (see make_sm_partition); SDRB_SM_PARTITION=0 keeps plain priority streams
+        const char* pe = getenv("SDRB_SM_PARTITION");
+        const bool want_part = !(pe && atoi(pe) == 0);
+        if (!(want_part && make_sm_partition(c, c->pll_max_ctas, prio_lo, prio_hi))) {
+            for (cudaStream_t* st : {&c->s_front, &c->s_back}) TRYCU(cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio_lo));
+            TRYCU(cudaStreamCreateWithPriority(&c->s_pll, cudaStreamNonBlocking, prio_hi));
+        }
     }
     for (cudaEvent_t* e : {&c->ev_in, &c->ev_join, &c->ev_h2d[0], &c->ev_h2d[1], &c->ev_consumed[0], &c->ev_consumed[1]}) TRYCU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (int i = 0; i < kNRing; i++)
@@ -1101,6 +1188,13 @@ int sdrb_chain_kernel_times(sdrb_chain* c, const char** names, float* ms, int ca
         k++;
     }
     *n = k;
+    return SDRB_OK;
+}
+
+int sdrb_chain_sm_partition(const sdrb_chain* c, int sms[2]) {
+    if (!c || !sms) return fail(SDRB_ERR_INVALID, "null argument");
+    sms[0] = c->part_pll_sms;
+    sms[1] = c->part_fir_sms;
     return SDRB_OK;
 }
 

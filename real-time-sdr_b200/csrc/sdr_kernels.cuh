@@ -644,6 +644,7 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
     float4* o4 = reinterpret_cast<float4*>(out);
     cr::PllK kk;
     cr::pll_k_load(kk);
+    cr::PllHead hd{0.0, 0u, 0u};
     // Loop shape (measured, profiles/README.md): tiles outside and chunks inside, so the common path has no branch
     // around the tile staging (a taken branch costs ~16 cycles of instruction fetch on a warp that has its scheduler to
     // itself); the chunk loop unrolled by two (half the loop branches and state-rotation moves; by four or more the
@@ -658,6 +659,9 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
         if (t == 0) {
             vc = cur[0];
             q0 = pll_recip(vc.x); q1 = pll_recip(vc.y); q2 = pll_recip(vc.z); q3 = pll_recip(vc.w);
+#if !defined(SDRB_PLL_UNROTATED)
+            cr::pll_chunk4r_prime(vc.x, q0, f, kk, hd);
+#endif
         }
         const int gend = min(nc, kPllTileChunks * (t + 1));
 #pragma unroll 2
@@ -669,13 +673,22 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
             const float4 vn = *(j + 1 < kPllTileChunks ? cur + j + 1 : nxt);
             const double p0 = pll_recip(vn.x), p1 = pll_recip(vn.y), p2 = pll_recip(vn.z), p3 = pll_recip(vn.w);
             float4 o;
+#if defined(SDRB_PLL_UNROTATED)
             cr::pll_chunk4(vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, f, k, kk, tab, o.x, o.y, o.z, o.w, lp.redo);
+#else
+            // rotated: this chunk's first phase detector was evaluated by the previous call, the next chunk's is evaluated
+            // here before the acceptance flag is branched on (pllmath.cuh: pll_chunk4r)
+            cr::pll_chunk4r(vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, vn.x, p0, f, hd, k, kk, tab, o.x, o.y, o.z, o.w, lp.redo);
+#endif
             o4[g] = o;
             vc = vn;
             q0 = p0; q1 = p1; q2 = p2; q3 = p3;
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#if !defined(SDRB_PLL_UNROTATED)
+    if (!f.generic_next) cr::pll_fast_resync(f, k);  // the rotated loop leaves sa / cr without their tie test
+#endif
     for (int i = n4; i < a.n; i++) out[i] = cr::pll_step_fast(x[i], cr::pll_guard_recip(x[i], pll_recip(x[i])), f, k, tab);
     // tail -> halo of the next slot
     float* nh = lp.trig.nxt + (size_t)s * lp.trig.pitch;

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -119,6 +120,7 @@ void crh_pll(const float* in, int n, float freq, float Fs, float scale, float ad
 // to the general atan2 / sincos (stats[0], stats[1]).
 void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, float adjust, float bw, float* out,
                   float* st4, double* trig, uint64_t* stats) {
+    const bool unrotated = getenv("SDRB_PLL_UNROTATED") != nullptr;  // the round-1 chunk (pll_chunk4), kept for comparison
     PllCoef k = pll_coef(freq, Fs, scale, adjust, bw);
     PllState st{st4[0], st4[1], st4[2], st4[3], *trig};
     PllFast f;
@@ -128,17 +130,33 @@ void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, flo
     PllK kk;
     pll_k_load(kk);
     int i = 0;
-    for (; i + 4 <= n; i += 4) {  // the kernel's chunking: 4 speculative steps, verified once
-        float c[4] = {in[i], in[i + 1], in[i + 2], in[i + 3]}, th[4];
-        auto recip = [](float v) { return 1.0 / fabs((double)v); };  // device: rcp.approx.ftz of |v|; the step itself rejects out-of-range samples
-        double r[4] = {recip(c[0]), recip(c[1]), recip(c[2]), recip(c[3])};
-        PllFast probe = f;
-        unsigned bad = f.generic_next ? 1u : 0u;
-        for (int j = 0; j < 4; j++) pll_step_spec(c[j], r[j], probe, k, kk, bad);
-        if (bad) gen_atan++;  // chunks that needed the careful path
-        pll_chunk4(c[0], c[1], c[2], c[3], r[0], r[1], r[2], r[3], f, k, kk, kTab, th[0], th[1], th[2], th[3]);
-        if (f.generic_next) gen_sc++;
-        for (int j = 0; j < 4; j++) out[i + j + 1] = nco_out(th[j], k);
+    auto recip = [](float v) { return 1.0 / fabs((double)v); };  // device: rcp.approx.ftz of |v|; the chunk itself rejects out-of-range samples
+    if (unrotated) {
+        for (; i + 4 <= n; i += 4) {  // round-1 chunking: 4 speculative steps, verified once
+            float c[4] = {in[i], in[i + 1], in[i + 2], in[i + 3]}, th[4];
+            double r[4] = {recip(c[0]), recip(c[1]), recip(c[2]), recip(c[3])};
+            PllFast probe = f;
+            unsigned bad = f.generic_next ? 1u : 0u;
+            for (int j = 0; j < 4; j++) pll_step_spec(c[j], r[j], probe, k, kk, bad);
+            if (bad) gen_atan++;  // chunks that needed the careful path
+            pll_chunk4(c[0], c[1], c[2], c[3], r[0], r[1], r[2], r[3], f, k, kk, kTab, th[0], th[1], th[2], th[3]);
+            if (f.generic_next) gen_sc++;
+            for (int j = 0; j < 4; j++) out[i + j + 1] = nco_out(th[j], k);
+        }
+    } else if (n >= 4) {  // the kernel's loop: rotated chunks, the next chunk's first phase detector evaluated ahead
+        PllHead h;
+        pll_chunk4r_prime(in[0], recip(in[0]), f, kk, h);
+        for (; i + 4 <= n; i += 4) {
+            float c[4] = {in[i], in[i + 1], in[i + 2], in[i + 3]}, th[4];
+            double r[4] = {recip(c[0]), recip(c[1]), recip(c[2]), recip(c[3])};
+            const float n0 = i + 4 < n ? in[i + 4] : 1.0f;
+            unsigned long long redo = 0;
+            pll_chunk4r(c[0], c[1], c[2], c[3], r[0], r[1], r[2], r[3], n0, recip(n0), f, h, k, kk, kTab, th[0], th[1], th[2], th[3], &redo);
+            gen_atan += redo;
+            if (f.generic_next) gen_sc++;
+            for (int j = 0; j < 4; j++) out[i + j + 1] = nco_out(th[j], k);
+        }
+        if (!f.generic_next) pll_fast_resync(f, k);
     }
     for (; i < n; i++) {
         float th = pll_step_fast(in[i], pll_guard_recip(in[i], 1.0 / fabs((double)in[i])), f, k, kTab);

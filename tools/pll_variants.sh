@@ -8,7 +8,7 @@ mkdir -p gpurun_out build
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   LIB=$PWD/build/libsdr_b200_$name.so
-  if [ "$name" = "default" ]; then LIB=$PWD/real-time-sdr_b200/libsdr_b200.so; else
+  if [ "$name" = "default" ]; then LIB=$PWD/real-time-sdr_b200/libsdr_b200.so; elif [ -n "${PREBUILT:-}" ] && [ -f $LIB ]; then :; else
     /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
       -Xcompiler -fPIC,-ffp-contract=off -shared $flags -o $LIB \
       real-time-sdr_b200/csrc/sdr_chain.cu real-time-sdr_b200/csrc/sdr_design.cpp 2>>gpurun_out/variants.err || { echo "$name: build failed" >> $OUT; continue; }
