@@ -867,7 +867,7 @@ SDRB_HD float pll_spec_tail(const PllHead& h, PllFast& f, const PllCoef& k, cons
     f.integ = fadd(f.integ, fmul(k.Ki, errorD));
     f.phase = fadd(fadd(f.phase, fmul(k.Kp, errorD)), f.integ);
     f.trigOffset = dadd(f.trigOffset, 1.0);
-    const double phd = (double)f.phase;
+    const double phd = (double)f.phase;  // F2F, ~20 cycles; integer forms need three dependent operations for a signed phase (measured slower)
     const double td = dadd(dmul(k.w, f.trigOffset), phd);
     const double xd = dadd(dadd(td, f.magic), -f.magic);  // (double)(float)td, see pll_step_spec
     const double tm = dfma(xd, kk.v[kK2OverPi], kMagicRint);
@@ -942,17 +942,17 @@ SDRB_HD void pll_chunk4(float i0, float i1, float i2, float i3, double r0, doubl
 // the head is a pure function and its result is then never used).  `first` (0/1): the state did not come out of a
 // speculative step (start of a block, after a careful repeat) and says generic_next.
 SDRB_HD void pll_chunk4r_prime(float i0, double r0, const PllFast& f, const PllK& kk, PllHead& h) { h = pll_spec_head(i0, r0, f, kk); }
-SDRB_HD void pll_chunk4r(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, float n0, double rn0,
-                         PllFast& f, PllHead& h, const PllCoef& k, const PllK& kk, const AtanTab& tab, float& t0, float& t1,
-                         float& t2, float& t3, unsigned long long* redo_ctr = nullptr) {
-    const PllFast saved = f;
-    unsigned bad = SDRB_BAD(f.generic_next, 8);
+// The speculative part of a chunk: four tails and heads; `h` is the head of the first sample and sa0 / cr0 the values it was
+// computed from, `hn` receives the head of the sample after the chunk (n0 / rn0), which the next call tests.
+SDRB_HD void pll_chunk4r_core(float i0, float i1, float i2, float i3, double r1, double r2, double r3, float n0, double rn0, PllFast& f,
+                              double sa0, double cr0, const PllHead& h, PllHead& hn, const PllCoef& k, const PllK& kk, float& t0,
+                              float& t1, float& t2, float& t3, unsigned& bad) {
     // every |in| of the chunk within [2^-90, 2^90): min / max instead of four tests (a NaN input is dropped by fmin / fmax
     // and shows up as a NaN e, which the wrap test rejects; zero and subnormal inputs have an infinite reciprocal: same)
     const float mn = fminf(fminf(fabsf(i0), fabsf(i1)), fminf(fabsf(i2), fabsf(i3)));
     const float mx = fmaxf(fmaxf(fabsf(i0), fabsf(i1)), fmaxf(fabsf(i2), fabsf(i3)));
     bad |= SDRB_BAD(!(mn >= 0x1p-90f), 0) | SDRB_BAD(!(mx < 0x1p90f), 0);
-    pll_spec_head_tests(h, saved.sa, saved.cr, bad);
+    pll_spec_head_tests(h, sa0, cr0, bad);
     t0 = pll_spec_tail(h, f, k, kk, bad);
     PllHead g = pll_spec_head(i1, r1, f, kk);
     pll_spec_head_tests(g, f.sa, f.cr, bad);
@@ -963,24 +963,45 @@ SDRB_HD void pll_chunk4r(float i0, float i1, float i2, float i3, double r0, doub
     g = pll_spec_head(i3, r3, f, kk);
     pll_spec_head_tests(g, f.sa, f.cr, bad);
     t3 = pll_spec_tail(g, f, k, kk, bad);
-    PllHead hn = pll_spec_head(n0, rn0, f, kk);  // tested by the next call
-    if (SDRB_UNLIKELY(bad != 0u)) {
+    hn = pll_spec_head(n0, rn0, f, kk);
+}
+// One chunk: returns the acceptance flag; `saved` receives the state before the chunk (what the careful repeat starts from).
+SDRB_HD unsigned pll_chunk4r_spec(float i0, float i1, float i2, float i3, double r1, double r2, double r3, float n0, double rn0, PllFast& f,
+                                  PllFast& saved, const PllHead& h, PllHead& hn, const PllCoef& k, const PllK& kk, float& t0, float& t1,
+                                  float& t2, float& t3) {
+    saved = f;
+    unsigned bad = SDRB_BAD(f.generic_next, 8);
+    pll_chunk4r_core(i0, i1, i2, i3, r1, r2, r3, n0, rn0, f, saved.sa, saved.cr, h, hn, k, kk, t0, t1, t2, t3, bad);
+    return bad;
+}
+// The careful repeat of a chunk whose flag was raised (`bad` only selects the diagnostic counters).
+SDRB_HD void pll_chunk4r_redo(unsigned bad, float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, float n0,
+                              double rn0, PllFast& f, const PllFast& saved, PllHead& hn, const PllCoef& k, const PllK& kk,
+                              const AtanTab& tab, float& t0, float& t1, float& t2, float& t3, unsigned long long* redo_ctr) {
 #if defined(__CUDA_ARCH__)
-        if (redo_ctr) atomicAdd(redo_ctr, 1ull);
+    if (redo_ctr) atomicAdd(redo_ctr, 1ull);
 #if defined(SDRB_PLL_DIAG)
-        for (int b = 0; b < 9; b++)
-            if ((bad >> b) & 1u) atomicAdd(redo_ctr + 2 * (1 + b), 1ull);
+    for (int b = 0; b < 9; b++)
+        if ((bad >> b) & 1u) atomicAdd(redo_ctr + 2 * (1 + b), 1ull);
 #endif
 #else
-        if (redo_ctr) ++*redo_ctr;
+    if (redo_ctr) ++*redo_ctr;
 #endif
-        PllFast again = saved;
-        float a0, a1, a2, a3;
-        pll_redo4(i0, i1, i2, i3, r0, r1, r2, r3, again, k, tab, a0, a1, a2, a3);
-        f = again;
-        t0 = a0; t1 = a1; t2 = a2; t3 = a3;
-        hn = pll_spec_head(n0, rn0, f, kk);
-    }
+    (void)bad;
+    PllFast again = saved;
+    float a0, a1, a2, a3;
+    pll_redo4(i0, i1, i2, i3, r0, r1, r2, r3, again, k, tab, a0, a1, a2, a3);
+    f = again;
+    t0 = a0; t1 = a1; t2 = a2; t3 = a3;
+    hn = pll_spec_head(n0, rn0, f, kk);
+}
+SDRB_HD void pll_chunk4r(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, float n0, double rn0,
+                         PllFast& f, PllHead& h, const PllCoef& k, const PllK& kk, const AtanTab& tab, float& t0, float& t1,
+                         float& t2, float& t3, unsigned long long* redo_ctr = nullptr) {
+    PllFast saved;
+    PllHead hn;
+    const unsigned bad = pll_chunk4r_spec(i0, i1, i2, i3, r1, r2, r3, n0, rn0, f, saved, h, hn, k, kk, t0, t1, t2, t3);
+    if (bad) pll_chunk4r_redo(bad, i0, i1, i2, i3, r0, r1, r2, r3, n0, rn0, f, saved, hn, k, kk, tab, t0, t1, t2, t3, redo_ctr);
     h = hn;
 }
 

@@ -585,6 +585,10 @@ constexpr int kPllTileRow = 4 * kPllTileChunks + 4;
 #ifndef SDRB_PLL_RING
 #define SDRB_PLL_RING 3
 #endif
+#ifndef SDRB_PLL_CHUNK_UNROLL
+#define SDRB_PLL_CHUNK_UNROLL 2  // chunks of four samples per loop iteration
+#endif
+constexpr int kPllChunkUnroll = SDRB_PLL_CHUNK_UNROLL;
 constexpr int kPllRing = SDRB_PLL_RING;  // tiles in the input ring; kPllRing - 1 of them are in flight ahead of the loop
 constexpr size_t pll_tile_bytes(int threads) { return sizeof(float) * kPllRing * threads * kPllTileRow; }
 // The launch asks for (nearly) all of an SM's shared memory, far more than the input ring needs: no other CTA then fits
@@ -664,6 +668,7 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
 #endif
         }
         const int gend = min(nc, kPllTileChunks * (t + 1));
+#if defined(SDRB_PLL_UNROTATED) || defined(SDRB_PLL_INLINE_REDO)
 #pragma unroll 2
         for (; g < gend; g++) {
             // next chunk's samples and their reciprocals 1/in (needed by the rotated phase detector): independent of
@@ -676,14 +681,49 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
 #if defined(SDRB_PLL_UNROTATED)
             cr::pll_chunk4(vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, f, k, kk, tab, o.x, o.y, o.z, o.w, lp.redo);
 #else
-            // rotated: this chunk's first phase detector was evaluated by the previous call, the next chunk's is evaluated
-            // here before the acceptance flag is branched on (pllmath.cuh: pll_chunk4r)
             cr::pll_chunk4r(vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, vn.x, p0, f, hd, k, kk, tab, o.x, o.y, o.z, o.w, lp.redo);
 #endif
             o4[g] = o;
             vc = vn;
             q0 = p0; q1 = p1; q2 = p2; q3 = p3;
         }
+#else
+        // Rotated chunks (pllmath.cuh: pll_chunk4r_spec): this chunk's first phase detector was evaluated by the previous
+        // pass, the next chunk's is evaluated before the acceptance flag is looked at.  The careful repeat sits behind a
+        // warp-uniform loop exit (a vote), not inside the loop: the common path has no taken forward branch and no
+        // reconvergence barrier, which cost ~12 cycles per chunk on a warp that has its scheduler to itself.
+        // (Passes of eight samples under one vote were built and measured 6 % slower, unrolled or not: profiles/README.md.)
+        while (g < gend) {
+            float4 o, vn;
+            double p0, p1, p2, p3;
+            cr::PllFast saved;
+            cr::PllHead hn;
+            unsigned bad = 0;
+#pragma unroll kPllChunkUnroll
+            for (; g < gend; g++) {
+                // next chunk's samples and their reciprocals 1/in: independent of the loop state, they fill the issue slots
+                // the dependent chain leaves empty.  (Past the last chunk of the block this reads stale bytes of the ring,
+                // which are never used.)
+                const int j = g & (kPllTileChunks - 1);
+                vn = *(j + 1 < kPllTileChunks ? cur + j + 1 : nxt);
+                p0 = pll_recip(vn.x); p1 = pll_recip(vn.y); p2 = pll_recip(vn.z); p3 = pll_recip(vn.w);
+                bad = cr::pll_chunk4r_spec(vc.x, vc.y, vc.z, vc.w, q1, q2, q3, vn.x, p0, f, saved, hd, hn, k, kk, o.x, o.y, o.z, o.w);
+                if (__any_sync(0xFFFFFFFFu, bad != 0u)) break;
+                o4[g] = o;
+                hd = hn;
+                vc = vn;
+                q0 = p0; q1 = p1; q2 = p2; q3 = p3;
+            }
+            if (g < gend) {  // left through the break: some lanes repeat chunk g on the careful path, the others keep their results
+                if (bad) cr::pll_chunk4r_redo(bad, vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, vn.x, p0, f, saved, hn, k, kk, tab, o.x, o.y, o.z, o.w, lp.redo);
+                o4[g] = o;
+                hd = hn;
+                vc = vn;
+                q0 = p0; q1 = p1; q2 = p2; q3 = p3;
+                g++;
+            }
+        }
+#endif
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #if !defined(SDRB_PLL_UNROTATED)

@@ -47,8 +47,9 @@ def main():
         if m and int(m.group(1), 16) < a:
             j = by_addr[int(m.group(1), 16)]
             cands.append((sum(1 for k in range(j, i) if opname(ins[k][1]) == "DFMA"), j, i))
-    top = max(c[0] for c in cands)
-    _, lo, hi = min((c for c in cands if c[0] >= 0.4 * top), key=lambda c: c[2] - c[1])  # innermost loop that holds the recurrence
+    # the innermost loop that holds the recurrence: dense in DFMA (the careful path around it is integer code), smallest span
+    dense = [c for c in cands if c[0] >= 60 and c[0] >= 0.12 * (c[2] - c[1])]
+    _, lo, hi = min(dense, key=lambda c: c[2] - c[1])
     t, bar, i, taken, n_issued, rows = 0, [0] * 6, lo, 0, 0, []
     per_op = {}
     while i <= hi:

@@ -91,6 +91,39 @@ __global__ void tput_kernel(float seed, long long* cycles, float* sink, unsigned
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// FP64 issue rate of ONE warp with `lanes` active lanes: 8 independent DFMA chains per thread.  (Does a half-empty warp
+// pass through the 16-lane FP64 pipe in one cycle instead of two?  It decides whether k_pll should run 16 stations per warp.)
+__global__ void dp_tput_kernel(int lanes, double seed, long long* cycles, double* sink) {
+    if ((int)threadIdx.x >= lanes) return;
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = seed + j;
+    const double e = seed * 0.5 + 1.0;
+    long long t0 = clock64();
+#pragma unroll 4
+    for (int i = 0; i < 1024; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = __fma_rn(a[j], e, e);
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += a[j];
+    sink[threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+int run_dp_tput(int lanes) {
+    long long* cyc; double* sink;
+    CK(cudaMalloc(&cyc, 8)); CK(cudaMalloc(&sink, 8 * 32));
+    dp_tput_kernel<<<1, 32>>>(lanes, 1.000001, cyc, sink);
+    dp_tput_kernel<<<1, 32>>>(lanes, 1.000001, cyc, sink);
+    CK(cudaDeviceSynchronize());
+    long long h; CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("{\"ubench\": \"fp64 issue, one warp\", \"active_lanes\": %d, \"cycles_per_dfma\": %.2f}\n", lanes, (double)h / (1024 * 8));
+    cudaFree(cyc); cudaFree(sink);
+    return 0;
+}
+
 template <int OP>
 int run_lat(const char* name, int instr_per_iter) {
     long long* cyc; double* sink;
@@ -129,6 +162,7 @@ int main() {
     run_lat<3>("dfma", 1); run_lat<4>("dadd", 1); run_lat<5>("dmul", 1);
     run_lat<6>("ddiv_rn+dadd", 2); run_lat<7>("f2f_d2f+f2f_f2d+dadd", 3); run_lat<8>("dmul+drint", 2);
     run_lat<9>("rcp64h+dadd", 2); run_lat<10>("fast_fdiv+fadd", 3); run_lat<11>("lop64+dadd", 2);
+    for (int l : {32, 16, 8}) run_dp_tput(l);
     for (int w : {4, 8, 16, 32}) {
         run_tput<0>("fmul+fadd", w); run_tput<1>("ffma", w); run_tput<2>("ffma2(h,x,-0)+fadd2 (unfused packed MAC)", w); run_tput<3>("fma.f32x2", w);
     }
