@@ -150,6 +150,24 @@ SDRB_HD double K(PllConst i) {
 #endif
 }
 
+// Leaner kernels for the speculative steps of the batched loop: sin r = r + r z (L1 + .. + L5 z^4), cos r = 1 - z/2 +
+// z^2 (M1 + .. + M5 z^4) on |r| <= pi/4, one coefficient less than fdlibm's each (Remez fits, tests/gen_pllmath_consts.py;
+// relative error below 2^-46.3 and 2^-50 including the rounding of the evaluation, checked against mpmath in tests/test_pllmath.py).  The FP64 pipe issues one warp
+// instruction per 2.3 cycles and the two kernels are its busiest stretch of the recurrence: every operation less is that
+// much off the chain.  The errors stay inside what the acceptance tests of the speculative step allow (2^-45 for the
+// float roundings of sa / cr with the 512-ulp tie window used there, 2^-45 absolute for e).
+#define SDRB_PLL_LEAN_CONSTS                                                                                     \
+    {0x1.1111110cdbeb5p-7, -0x1.5555555552e41p-3, 0x1.71d752f9f8bdfp-19, -0x1.a019f946a7019p-13, -0x1.a950938183dcbp-26, \
+     0.0, -0x1.6c16c169ae93cp-10, 0x1.5555555554a28p-5, -0x1.27e1089e1a501p-22, 0x1.a019fcd9727a0p-16, 0x1.1c065229821d1p-29, \
+     0.0, 0x1.45f306dc9c883p-1, 0x1.1a62633145c07p-54, 0x1.921fb54442d18p+0}
+// same layout as PllConst: kS2 = L2, kS1 = L1, kS4 = L4, kS3 = L3, kS6 = L5 (!), kS5 unused, kC2 = M2, kC1 = M1, kC4 = M4, kC3 = M3,
+// kC6 = M5 (!), kC5 unused
+enum PllLeanConst { kL5 = kS6, kM5 = kC6 };
+#if defined(__CUDACC__)
+__device__ double g_pll_lean_consts[15] = SDRB_PLL_LEAN_CONSTS;
+#endif
+static const double h_pll_lean_consts[15] = SDRB_PLL_LEAN_CONSTS;
+
 // The same constants pinned in registers for the batched PLL kernel: left to itself the compiler re-reads the
 // constant bank inside the loop (28 LDC per 8 samples, each an issue slot of an in-order warp that has none to spare).
 // They are read once through a volatile global load, which cannot be rematerialised.
@@ -166,6 +184,20 @@ SDRB_HD void pll_k_load(PllK& kk) {
         asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(kk.v[i]) : "l"(&g_pll_consts[i]));
 #else
         kk.v[i] = h_pll_consts[i];
+#endif
+    }
+}
+SDRB_HD void pll_k_load_lean(PllK& kk) {  // the lean kernels' coefficients (sincos_poly2_lean) and the reduction constants
+#pragma unroll
+    for (int i = 0; i < 15; i++) {
+        if (i == kS5 || i == kC5) {
+            kk.v[i] = 0.0;
+            continue;
+        }
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(kk.v[i]) : "l"(&g_pll_lean_consts[i]));
+#else
+        kk.v[i] = h_pll_lean_consts[i];
 #endif
     }
 }
@@ -261,6 +293,25 @@ SDRB_HD void sincos_poly2k(double r, double rs, double& sr, double& cr_, const P
     const double cA = dfma(z2, c12, ch);
     const double z4 = dmul(z2, z2);
     const double cC = dfma(z2, c56, c34);
+    cr_ = dfma(z4, cC, cA);
+}
+// the lean kernels (coefficients from pll_k_load_lean): 16 operations instead of 18, same dependent depth
+SDRB_HD void sincos_poly2_lean(double r, double rs, double& sr, double& cr_, const PllK& kk) {
+    const double z = dmul(r, r);
+    const double z2 = dmul(z, z);
+    const double rz = dmul(rs, z);
+    const double s12 = dfma(kk.v[kS2], z, kk.v[kS1]);
+    const double s34 = dfma(kk.v[kS4], z, kk.v[kS3]);
+    const double sA = dfma(rz, s12, rs);
+    const double sB = dmul(rz, z2);
+    const double sC = dfma(z2, kk.v[kL5], s34);
+    sr = dfma(sB, sC, sA);
+    const double c12 = dfma(kk.v[kC2], z, kk.v[kC1]);
+    const double c34 = dfma(kk.v[kC4], z, kk.v[kC3]);
+    const double ch = dfma(-0.5, z, 1.0);
+    const double cA = dfma(z2, c12, ch);
+    const double z4 = dmul(z2, z2);
+    const double cC = dfma(z2, kk.v[kM5], c34);
     cr_ = dfma(z4, cC, cA);
 }
 SDRB_HD double flip_sign_if(double v, unsigned flip) {  // exact negation by a sign-bit XOR (one integer op on the chain)
@@ -825,7 +876,7 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
 // The tests are leaner than pll_step_spec's (same guarantees, fewer instructions beside the chain):
 //   e   : RN_f(e - 2^-43) == RN_f(e + 2^-43), i.e. no float rounding step within the error bound of e, whatever its
 //         binade; replaces the exponent-dependent window of ambig_abs (and rejects |e| < ~2^-19 by itself);
-//   sa,cr : low 29 bits within 256 of the tie pattern, as one add and one masked compare;
+//   sa,cr : low 29 bits within 512 of the tie pattern (the lean kernels are good to 2^-46.6), as one add and one masked compare;
 //   td  : exponent field against the one stored with the magic constant (one masked compare);
 //   in  : the range test is made once per chunk on min / max of the four inputs (pll_chunk4r).
 struct PllHead {
@@ -833,8 +884,8 @@ struct PllHead {
     uint32_t Ke, bh;  // bh: high word of base (for the +-2 test)
 };
 constexpr double kAtanTol = 0x1p-43;  // 2^kAtanTolLog2
-SDRB_HD unsigned ambig_tie29(double v) {  // low 29 bits in [tie - 256, tie + 255]
-    return (unsigned)((((dlo(v) + kAmbigUlps) & 0x1FFFFE00u) ^ 0x10000000u) == 0u);
+SDRB_HD unsigned ambig_tie29(double v) {  // low 29 bits in [tie - 512, tie + 511]: within 2^-44 relative of a float rounding tie
+    return (unsigned)((((dlo(v) + 2u * kAmbigUlps) & 0x1FFFFC00u) ^ 0x10000000u) == 0u);
 }
 SDRB_HD PllHead pll_spec_head(float in, double rin, const PllFast& f, const PllK& kk) {
     const uint32_t rhi = dhi(f.r);
@@ -876,7 +927,7 @@ SDRB_HD float pll_spec_tail(const PllHead& h, PllFast& f, const PllCoef& k, cons
     const double r = dfma(-kd, kk.v[kKPio2M], dfma(-kd, kk.v[kKPio2H], xd));
     const uint32_t rah = dhi(r) & 0x7FFFFFFFu;
     double sa, cr_;
-    sincos_poly2k(r, mkd(rah, dlo(r)), sa, cr_, kk);
+    sincos_poly2_lean(r, mkd(rah, dlo(r)), sa, cr_, kk);  // kk from pll_k_load_lean
     // td left the binade of the magic constant; r tiny.  (sa / cr near a float tie: tested by the head that uses them.)
     bad |= SDRB_BAD(((dhi(td) & 0x7FF00000u) ^ f.texp) != 0u, 4) | SDRB_BAD(rah < f.rmin_hi, 5);
     f.sa = sa;

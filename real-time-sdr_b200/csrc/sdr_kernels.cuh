@@ -647,8 +647,14 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
     double q0 = 1.0, q1 = 1.0, q2 = 1.0, q3 = 1.0;
     float4* o4 = reinterpret_cast<float4*>(out);
     cr::PllK kk;
+#if defined(SDRB_PLL_UNROTATED)
     cr::pll_k_load(kk);
+#else
+    cr::pll_k_load_lean(kk);
+#endif
     cr::PllHead hd{0.0, 0u, 0u};
+    [[maybe_unused]] float4 op = make_float4(0.f, 0.f, 0.f, 0.f);  // NCO phases of the last accepted chunk, not stored yet
+    [[maybe_unused]] bool pending = false;
     // Loop shape (measured, profiles/README.md): tiles outside and chunks inside, so the common path has no branch
     // around the tile staging (a taken branch costs ~16 cycles of instruction fetch on a warp that has its scheduler to
     // itself); the chunk loop unrolled by two (half the loop branches and state-rotation moves; by four or more the
@@ -707,15 +713,26 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
                 const int j = g & (kPllTileChunks - 1);
                 vn = *(j + 1 < kPllTileChunks ? cur + j + 1 : nxt);
                 p0 = pll_recip(vn.x); p1 = pll_recip(vn.y); p2 = pll_recip(vn.z); p3 = pll_recip(vn.w);
+#if defined(SDRB_PLL_DEFER_STORE)
+                if (pending) o4[g - 1] = op;
+#endif
                 bad = cr::pll_chunk4r_spec(vc.x, vc.y, vc.z, vc.w, q1, q2, q3, vn.x, p0, f, saved, hd, hn, k, kk, o.x, o.y, o.z, o.w);
                 if (__any_sync(0xFFFFFFFFu, bad != 0u)) break;
+#if defined(SDRB_PLL_DEFER_STORE)
+                op = o; pending = true;
+#else
                 o4[g] = o;
+#endif
                 hd = hn;
                 vc = vn;
                 q0 = p0; q1 = p1; q2 = p2; q3 = p3;
             }
             if (g < gend) {  // left through the break: some lanes repeat chunk g on the careful path, the others keep their results
                 if (bad) cr::pll_chunk4r_redo(bad, vc.x, vc.y, vc.z, vc.w, q0, q1, q2, q3, vn.x, p0, f, saved, hn, k, kk, tab, o.x, o.y, o.z, o.w, lp.redo);
+#if defined(SDRB_PLL_DEFER_STORE)
+                if (pending) o4[g - 1] = op;
+                pending = false;
+#endif
                 o4[g] = o;
                 hd = hn;
                 vc = vn;
@@ -726,6 +743,9 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
 #endif
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#if defined(SDRB_PLL_DEFER_STORE)
+    if (pending) o4[g - 1] = op;
+#endif
 #if !defined(SDRB_PLL_UNROTATED)
     if (!f.generic_next) cr::pll_fast_resync(f, k);  // the rotated loop leaves sa / cr without their tie test
 #endif

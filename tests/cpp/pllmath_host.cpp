@@ -19,6 +19,12 @@ static uint32_t f2bits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
 
 extern "C" {
 
+// the lean sine / cosine kernels of the speculative PLL step on reduced arguments (|r| <= pi/4), as doubles
+void crh_poly_lean(const double* r, int n, double* s, double* c) {
+    PllK kk;
+    pll_k_load_lean(kk);
+    for (int i = 0; i < n; i++) sincos_poly2_lean(r[i], fabs(r[i]), s[i], c[i], kk);
+}
 void crh_sincos(const float* t, int n, float* s, float* c) { for (int i = 0; i < n; i++) sincos_f(t[i], s[i], c[i]); }
 void crh_cos(const float* t, int n, float* c) { for (int i = 0; i < n; i++) c[i] = cos_f(t[i]); }
 void crh_cos_lean(const float* t, int n, float* c) { for (int i = 0; i < n; i++) c[i] = cos_lean_f(t[i]); }
@@ -128,7 +134,7 @@ void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, flo
     out[0] = out[n];
     uint64_t gen_atan = 0, gen_sc = 0;
     PllK kk;
-    pll_k_load(kk);
+    if (unrotated) pll_k_load(kk); else pll_k_load_lean(kk);
     int i = 0;
     auto recip = [](float v) { return 1.0 / fabs((double)v); };  // device: rcp.approx.ftz of |v|; the chunk itself rejects out-of-range samples
     if (unrotated) {

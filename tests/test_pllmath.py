@@ -223,3 +223,26 @@ def test_fast_recurrence_at_large_phase(host, oracle, oracle_mod, freq, scale, b
     # (Round 1 sent the "input sign opposite to the NCO's, quadrant 0 or 2" case to the careful path: right values, 6x the time.)
     chunks = nb * (n // 4)
     assert stats[0] < 0.005 * chunks, f"{stats[0]} of {chunks} chunks left the fast path"
+
+
+def test_lean_kernels_error_bound(host):
+    """The speculative PLL step evaluates sin / cos of the reduced phase with kernels one coefficient shorter than fdlibm's
+    (pllmath.cuh: sincos_poly2_lean).  Its acceptance tests assume a relative error below 2^-45 (512-ulp tie window for the
+    float roundings of sa / cr); the kernels must stay inside that with margin, over the whole reduced range."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    host.crh_poly_lean.argtypes = [f64p, C.c_int, f64p, f64p]
+    rng = np.random.default_rng(5)
+    r = np.concatenate([np.linspace(1e-9, np.pi / 4, 6001), rng.random(6000) * (np.pi / 4), np.array([np.pi / 4 * (1 + 2.0 ** -50), 2.0 ** -30, 2.0 ** -12])])
+    r = np.concatenate([r, -r]).astype(np.float64)
+    s = np.zeros_like(r)
+    c = np.zeros_like(r)
+    host.crh_poly_lean(r, r.size, s, c)
+    worst_s = worst_c = mp.mpf(0)
+    for ri, si, ci in zip(r, s, c):
+        x = mp.mpf(float(ri))
+        worst_s = max(worst_s, abs((mp.mpf(float(si)) - mp.sin(abs(x))) / mp.sin(abs(x))))  # the kernel returns sin |r|
+        worst_c = max(worst_c, abs((mp.mpf(float(ci)) - mp.cos(x)) / mp.cos(x)))
+    assert worst_s < mp.mpf(2) ** -46.3, float(mp.log(worst_s, 2))
+    assert worst_c < mp.mpf(2) ** -50, float(mp.log(worst_c, 2))  # approximation 2^-51.5 plus the rounding of the evaluation
