@@ -287,8 +287,9 @@ int sdrb_chain_pll_redo_detail(sdrb_chain* c, unsigned long long counts[20]);
  * frame-sync call); a non-zero count means data was cut off and says where. */
 int sdrb_chain_rds_overflows(sdrb_chain* c, unsigned int counts[3]);
 /* SM partition of the overlap-mode streams: sms[0] SMs owned by the PLL stream, sms[1] by the front- and back-end streams
- * (CUDA green contexts, created with the chain).  Both 0 when the driver refused or the environment
- * variable SDRB_SM_PARTITION=0 was set: the chain then runs on ordinary priority streams, with identical results. */
+ * (CUDA green contexts, created with the chain while the PLL bounds the step, i.e. up to 1024 stereo+RDS stations; see
+ * DESIGN.md 5).  Both 0 for larger batches, when the driver refused, or with the environment variable SDRB_SM_PARTITION=0
+ * (1 forces the partition on): the chain then runs on ordinary priority streams, with identical results. */
 int sdrb_chain_sm_partition(const sdrb_chain* c, int sms[2]);
 /* Number of kernels launched by this chain so far. */
 long long sdrb_chain_launch_count(const sdrb_chain* c);

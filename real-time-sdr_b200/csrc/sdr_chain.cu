@@ -666,8 +666,12 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         TRYCU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         for (cudaStream_t* st : {&c->s_h2d, &c->s_d2h}) TRYCU(cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio_lo));
         // SM partition for the overlap-mode streams (see make_sm_partition); SDRB_SM_PARTITION=0 keeps plain priority streams
+        // Only while the PLL is the longer side of a step (at most two of its warps per SM of the partition: 1024 stereo+RDS
+        // stations).  Larger batches are bound by the FIR kernels, which then want the PLL's SMs whenever it is idle
+        // (4096 stations: 2.47 ms per step without the partition, 2.68 with it).  SDRB_SM_PARTITION=0 / 1 forces it off / on.
         const char* pe = getenv("SDRB_SM_PARTITION");
-        const bool want_part = !(pe && atoi(pe) == 0);
+        const int pll_warps = (cfg->n_streams + 31) / 32 * (cfg->type == 'r' ? 2 : 1);
+        const bool want_part = pe ? atoi(pe) != 0 : pll_warps <= 2 * c->pll_max_ctas;
         if (!(want_part && make_sm_partition(c, c->pll_max_ctas, prio_lo, prio_hi))) {
             for (cudaStream_t* st : {&c->s_front, &c->s_back}) TRYCU(cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, prio_lo));
             TRYCU(cudaStreamCreateWithPriority(&c->s_pll, cudaStreamNonBlocking, prio_hi));
