@@ -2,7 +2,8 @@
 
 Stations never exchange data: rank r owns a contiguous range of global station indices and all
 of their carried state; the only inter-rank traffic is the final gather of small per-station results (and, in bench.py,
-the timing barrier).  No collective touches the data path, so the same code runs over gloo on CPUs (tests) and nccl.
+the timing barrier).  No collective touches the data path, so the same code runs over gloo (tests) and nccl (rows are
+staged through the rank's GPU there).
 """
 from __future__ import annotations
 
@@ -35,11 +36,13 @@ def gather_rows(local: np.ndarray, rank: int, world: int, total: int, dist=None)
     pad = np.zeros((max(counts), width), local.dtype)
     pad[: local.shape[0]] = local.reshape(local.shape[0], width)
     t = torch.from_numpy(pad.view(np.uint8).reshape(-1).copy())
+    if dist.get_backend() == "nccl":  # NCCL moves device tensors only: stage the (small) rows through this rank's GPU
+        t = t.cuda()
     out = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
     dist.gather(t, out, dst=0)
     if rank != 0:
         return None
-    rows = [o.numpy().view(local.dtype).reshape(max(counts), width)[: counts[r]] for r, o in enumerate(out)]
+    rows = [o.cpu().numpy().view(local.dtype).reshape(max(counts), width)[: counts[r]] for r, o in enumerate(out)]
     return np.concatenate(rows).reshape((total,) + local.shape[1:])
 
 
