@@ -669,7 +669,23 @@ inline float cos_f_rare(float t) { return cos_f(t); }
 // the reduction instead of the 18 of both kernels.  The result is accepted when it is farther than 512 double-ulps (2^-44
 // relative) from a float rounding tie; anything doubtful (tie, tiny reduced argument, huge or non-finite phase) goes to
 // cos_f itself.  Checked against glibc on 5M arguments (tests/test_pllmath.py::test_lean_cosine_equals_glibc).
-SDRB_HD float cos_lean_f(float t) {
+// coefficient table of the unified chain, [parity][c5, c4, c3, c2, c1, c0, -, -]: row 0 (q even) the cosine's, row 1 the sine's
+#define SDRB_COS_LEAN_TAB                                                                                                        \
+    {0x1.1c065229821d1p-29, -0x1.27e1089e1a501p-22, 0x1.a019fcd9727a0p-16, -0x1.6c16c169ae93cp-10, 0x1.5555555554a28p-5, -0.5, 0.0, \
+     0.0, 0.0, -0x1.a950938183dcbp-26, 0x1.71d752f9f8bdfp-19, -0x1.a019f946a7019p-13, 0x1.1111110cdbeb5p-7, -0x1.5555555552e41p-3,   \
+     0.0, 0.0}
+static const double h_cos_lean_tab[16] = SDRB_COS_LEAN_TAB;
+#if defined(__CUDACC__)
+__device__ __constant__ double c_cos_lean_tab[16] = SDRB_COS_LEAN_TAB;
+#endif
+// `tab`: the table above in memory that every lane can index at its own row cheaply (k_mix keeps a copy in shared memory;
+// nullptr: the host table / the constant bank)
+SDRB_HD float cos_lean_f(float t, const double* tab = nullptr) {
+#if defined(__CUDA_ARCH__)
+    if (!tab) tab = c_cos_lean_tab;
+#else
+    if (!tab) tab = h_cos_lean_tab;
+#endif
     const double x = (double)t;
     const double tm = dfma(x, kTwoOverPi, kMagicRint);
     const double kd = dadd(tm, -kMagicRint);
@@ -677,26 +693,24 @@ SDRB_HD float cos_lean_f(float t) {
     const double r = dfma(-kd, kPio2M, dfma(-kd, kPio2H, x));
     const double z = dmul(r, r);
     const bool odd = (q & 1u) != 0u;
-    const double c5 = odd ? 0.0 : 0x1.1c065229821d1p-29;                      //  -    / M5
-    const double c4 = odd ? -0x1.a950938183dcbp-26 : -0x1.27e1089e1a501p-22;  //  L5   / M4
-    const double c3 = odd ? 0x1.71d752f9f8bdfp-19 : 0x1.a019fcd9727a0p-16;    //  L4   / M3
-    const double c2 = odd ? -0x1.a019f946a7019p-13 : -0x1.6c16c169ae93cp-10;  //  L3   / M2
-    const double c1 = odd ? 0x1.1111110cdbeb5p-7 : 0x1.5555555554a28p-5;      //  L2   / M1
-    const double c0 = odd ? -0x1.5555555552e41p-3 : -0.5;                     //  L1   / -1/2
+    const double* c = tab + 8 * (q & 1u);
     const double A = odd ? r : 1.0;
     const double B = odd ? dmul(r, z) : z;
-    double p = dfma(c5, z, c4);
-    p = dfma(p, z, c3);
-    p = dfma(p, z, c2);
-    p = dfma(p, z, c1);
-    p = dfma(p, z, c0);
+    double p = dfma(c[0], z, c[1]);
+    p = dfma(p, z, c[2]);
+    p = dfma(p, z, c[3]);
+    p = dfma(p, z, c[4]);
+    p = dfma(p, z, c[5]);
     const double v = dfma(B, p, A);  // cos r or sin r
     // sign: q = 0 -> +cos, 1 -> -sin, 2 -> -cos, 3 -> +sin
     const double dc = flip_sign_if(v, ((q + 1u) >> 1) & 1u);
-    const uint32_t low = dlo(dc) & 0x1FFFFFFFu;
-    const bool tie = ((low + 2u * kAmbigUlps) & 0x1FFFFC00u) == 0x10000000u;
-    const bool tiny = (kd != 0.0) && fabs(r) < reduce_rmin(kd);
-    if (!(fabs(x) < kReduceLimit) || tiny || tie || (dhi(dc) & 0x7FF00000u) < 0x38100000u) return cos_f_rare(t);
+    // the tests, on integer words: phase below 2^45 (also rejects inf / NaN); reduced argument not tiny for its quadrant
+    // count (reduce_rmin; a tiny r with k = 0 is harmless but rare enough to go the same way); result not within 512
+    // double-ulps of a float rounding tie
+    const bool big = (fbits(t) & 0x7FFFFFFFu) >= 0x56000000u;
+    const bool tiny = (dhi(r) & 0x7FFFFFFFu) < reduce_rmin_hi(x);
+    const bool tie = (((dlo(dc) & 0x1FFFFFFFu) + 2u * kAmbigUlps) & 0x1FFFFC00u) == 0x10000000u;
+    if (big || tiny || tie) return cos_f_rare(t);
     return (float)dc;
 }
 

@@ -782,14 +782,20 @@ struct MixArgs {
     int do_stereo;
 };
 
-constexpr int kMixPer = 4;  // consecutive samples per thread: all loads first, then the cosines
+#ifndef SDRB_MIX_PER
+#define SDRB_MIX_PER 4
+#endif
+#ifndef SDRB_MIX_MINB
+#define SDRB_MIX_MINB 4
+#endif
+constexpr int kMixPer = SDRB_MIX_PER;  // consecutive samples per thread: all loads first, then the cosines
 
 // One sample of the generic (bounds- and option-checked) form: the tail of a row and the stage-dumping parity runs.
-__device__ __forceinline__ void mix_one_checked(const MixArgs& a, int s, int i, bool rds) {
+__device__ __forceinline__ void mix_one_checked(const MixArgs& a, int s, int i, bool rds, const double* ctab) {
     const bool in_blk = i < a.n;
     if (a.do_stereo) {
         const float th = a.trig19[(size_t)s * a.trig19_pitch + i - 1];
-        const float car = cr::cos_lean_f(__fadd_rn(__fmul_rn(th, a.scale19), a.adjust19));
+        const float car = cr::cos_lean_f(__fadd_rn(__fmul_rn(th, a.scale19), a.adjust19), ctab);
         if (a.carrier_out) a.carrier_out[(size_t)s * (a.n + 1) + i] = car;
         if (in_blk) {
             const float band = a.band[(size_t)s * a.band_pitch + i];
@@ -798,7 +804,7 @@ __device__ __forceinline__ void mix_one_checked(const MixArgs& a, int s, int i, 
     }
     if (rds) {
         const float th = a.trig114[(size_t)s * a.trig114_pitch + i - 1];
-        const float ip = cr::cos_lean_f(__fadd_rn(__fmul_rn(th, a.scale114), a.adjust114));
+        const float ip = cr::cos_lean_f(__fadd_rn(__fmul_rn(th, a.scale114), a.adjust114), ctab);
         if (a.ipll_out) a.ipll_out[(size_t)s * (a.n + 1) + i] = ip;
         if (in_blk) {
             // the all-pass "delay" FIR (src/rds.cpp:122): 0 + 1*x[i-50] + 0*... == 0.0f + x[i-50]
@@ -812,34 +818,47 @@ __device__ __forceinline__ void mix_one_checked(const MixArgs& a, int s, int i, 
 // FAST: no stage dumps are requested and both mixers run (the production configuration): a thread whose kMixPer
 // samples lie inside the block and before the halo tail takes a path without a single bounds or option test.
 template <bool FAST>
-__global__ void __launch_bounds__(256) k_mix(const MixArgs a) {
+__global__ void __launch_bounds__(256, SDRB_MIX_MINB) k_mix(const MixArgs a) {
+    // the cosine's coefficient table where every lane can index its own row with one shared-memory load per coefficient
+    // (selecting twelve 32-bit immediates per cosine cost more instructions than the polynomial itself)
+    __shared__ double ctab[16];
+    if (threadIdx.x < 16) ctab[threadIdx.x] = cr::c_cos_lean_tab[threadIdx.x];
+    __syncthreads();
     const int s = blockIdx.y;
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * kMixPer;
     if (i0 > a.n) return;
     const bool rds = a.rds_band != nullptr;
     if (FAST && i0 + kMixPer <= a.n - max(a.stereo_dc.halo, a.rds_dc.halo)) {
-        const float* t19 = a.trig19 + (size_t)s * a.trig19_pitch + i0 - 1;
-        const float* bd = a.band + (size_t)s * a.band_pitch + i0;
-        const float* t114 = a.trig114 + (size_t)s * a.trig114_pitch + i0 - 1;
+        // Vector accesses (the rows are 16-byte aligned at sample 0 and i0 is a multiple of four): one float4 per band
+        // and output, two per NCO-phase row (the phase of sample i-1: the aligned quad before this one supplies [i0-1]),
+        // two float2 for the delayed RDS band (offset -50: 8-byte aligned).  Scalar accesses at a 16-byte lane stride kept
+        // the load/store unit busier than the issue slots (ncu: Mem Busy 63 %).
+        static_assert(kMixPer == 4, "the fast path of k_mix is written for four samples per thread");
+        const float* t19 = a.trig19 + (size_t)s * a.trig19_pitch + i0;
+        const float* t114 = a.trig114 + (size_t)s * a.trig114_pitch + i0;
         const float* rb = a.rds_band + (size_t)s * a.rds_band_pitch + i0 - 50;
-        float th19[kMixPer], band[kMixPer], th114[kMixPer], rbd[kMixPer];
+        const float4 bq = *reinterpret_cast<const float4*>(a.band + (size_t)s * a.band_pitch + i0);
+        const float4 p19 = *reinterpret_cast<const float4*>(t19 - 4), c19 = *reinterpret_cast<const float4*>(t19);
+        const float4 p114 = *reinterpret_cast<const float4*>(t114 - 4), c114 = *reinterpret_cast<const float4*>(t114);
+        const float2 r0 = *reinterpret_cast<const float2*>(rb), r1 = *reinterpret_cast<const float2*>(rb + 2);
+        const float th19[4] = {p19.w, c19.x, c19.y, c19.z}, band[4] = {bq.x, bq.y, bq.z, bq.w};
+        const float th114[4] = {p114.w, c114.x, c114.y, c114.z}, rbd[4] = {r0.x, r0.y, r1.x, r1.y};
+        float so[4], ro[4];
 #pragma unroll
-        for (int j = 0; j < kMixPer; j++) { th19[j] = t19[j]; band[j] = bd[j]; th114[j] = t114[j]; rbd[j] = rb[j]; }
-        float* sdc = a.stereo_dc.cur + (size_t)s * a.stereo_dc.pitch + i0;
-        float* rdc = a.rds_dc.cur + (size_t)s * a.rds_dc.pitch + i0;
-#pragma unroll
-        for (int j = 0; j < kMixPer; j++) {
-            const float car = cr::cos_lean_f(__fadd_rn(__fmul_rn(th19[j], a.scale19), a.adjust19));
-            sdc[j] = __double2float_rn(__dmul_rn(__dmul_rn(2.0, (double)band[j]), (double)car));
-            const float ip = cr::cos_lean_f(__fadd_rn(__fmul_rn(th114[j], a.scale114), a.adjust114));
-            rdc[j] = __fmul_rn(__fmul_rn(2.0f, __fadd_rn(0.0f, rbd[j])), ip);
+        for (int j = 0; j < 4; j++) {
+            const float car = cr::cos_lean_f(__fadd_rn(__fmul_rn(th19[j], a.scale19), a.adjust19), ctab);
+            so[j] = __double2float_rn(__dmul_rn(__dmul_rn(2.0, (double)band[j]), (double)car));
+            const float ip = cr::cos_lean_f(__fadd_rn(__fmul_rn(th114[j], a.scale114), a.adjust114), ctab);
+            ro[j] = __fmul_rn(__fmul_rn(2.0f, __fadd_rn(0.0f, rbd[j])), ip);
         }
+        *reinterpret_cast<float4*>(a.stereo_dc.cur + (size_t)s * a.stereo_dc.pitch + i0) = make_float4(so[0], so[1], so[2], so[3]);
+        *reinterpret_cast<float4*>(a.rds_dc.cur + (size_t)s * a.rds_dc.pitch + i0) = make_float4(ro[0], ro[1], ro[2], ro[3]);
         return;
     }
     for (int j = 0; j < kMixPer; j++) {
         const int i = i0 + j;
         if (i > a.n) break;
-        mix_one_checked(a, s, i, rds);
+        mix_one_checked(a, s, i, rds, ctab);
     }
 }
 
