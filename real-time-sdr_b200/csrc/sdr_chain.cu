@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -1264,9 +1265,47 @@ int sdrb_chain_rds_overflows(sdrb_chain* c, unsigned int counts[3]) {
 
 // ---- stand-alone batched primitives ---------------------------------------------------------------
 namespace {
-int upload_taps(const float* h_taps, int nh, float** d, cudaStream_t st) {
+// Taps of the stand-alone FIR calls live in a small per-process cache keyed by device and content: the reference-shaped
+// callers pass the same host vector block after block (src/rffrontend.cpp:66-67, src/stereo.cpp:74-97, src/rds.cpp:105-133),
+// so a device allocation, an upload and a free per call (round 1) were pure overhead.  An entry is uploaded once with a
+// blocking copy and never changes afterwards, which makes it safe to read from any stream.
+struct TapEntry {
+    int dev;
+    std::vector<float> host;
+    float* d;
+};
+std::mutex g_tap_mutex;
+std::vector<TapEntry> g_tap_cache;
+constexpr size_t kTapCacheEntries = 64;
+
+// *d: device taps; *owned: 1 if the caller has to cudaFreeAsync them on `st` (cache full: the round-1 path)
+int upload_taps(const float* h_taps, int nh, float** d, cudaStream_t st, int* owned) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    *owned = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_tap_mutex);
+        for (const TapEntry& e : g_tap_cache)
+            if (e.dev == dev && (int)e.host.size() == nh && memcmp(e.host.data(), h_taps, sizeof(float) * nh) == 0) {
+                *d = e.d;
+                return SDRB_OK;
+            }
+        if (g_tap_cache.size() < kTapCacheEntries) {
+            float* p = nullptr;
+            CU(cudaMalloc((void**)&p, sizeof(float) * nh));
+            cudaError_t e = cudaMemcpy(p, h_taps, sizeof(float) * nh, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                cudaFree(p);
+                return cuda_fail(e, "cudaMemcpy(taps)");
+            }
+            g_tap_cache.push_back(TapEntry{dev, std::vector<float>(h_taps, h_taps + nh), p});
+            *d = p;
+            return SDRB_OK;
+        }
+    }
     CU(cudaMallocAsync((void**)d, sizeof(float) * nh, st));
     CU(cudaMemcpyAsync(*d, h_taps, sizeof(float) * nh, cudaMemcpyHostToDevice, st));
+    *owned = 1;
     return SDRB_OK;
 }
 }  // namespace
@@ -1279,7 +1318,8 @@ int sdrb_fir_decim(const float* d_x, size_t x_pitch, int nx, const float* h_taps
     if (nx < nstate) return fail(SDRB_ERR_INVALID, "nx must be >= nh-1 (the reference reads out of bounds otherwise)");
     cudaStream_t st = (cudaStream_t)stream;
     float* d_h = nullptr;
-    int rc = upload_taps(h_taps, nh, &d_h, st);
+    int owned = 0;
+    int rc = upload_taps(h_taps, nh, &d_h, st, &owned);
     if (rc) return rc;
     const int ny = nx / decim;
     if (ny > 0) {
@@ -1291,7 +1331,7 @@ int sdrb_fir_decim(const float* d_x, size_t x_pitch, int nx, const float* h_taps
         k_state_update<<<grid, 128, 0, st>>>(d_x, x_pitch, nx, d_state, nstate);
     }
     CU(cudaGetLastError());
-    CU(cudaFreeAsync(d_h, st));
+    if (owned) CU(cudaFreeAsync(d_h, st));
     return SDRB_OK;
 }
 
@@ -1303,7 +1343,8 @@ int sdrb_fir_updown(const float* d_x, size_t x_pitch, int nx, const float* h_tap
     if (nstate < (nh - 1) / up) return fail(SDRB_ERR_INVALID, "nstate must be >= (nh-1)/up");
     cudaStream_t st = (cudaStream_t)stream;
     float* d_h = nullptr;
-    int rc = upload_taps(h_taps, nh, &d_h, st);
+    int owned = 0;
+    int rc = upload_taps(h_taps, nh, &d_h, st, &owned);
     if (rc) return rc;
     const int ny = (int)(((long long)nx * up) / down);
     if (ny > 0) {
@@ -1315,7 +1356,7 @@ int sdrb_fir_updown(const float* d_x, size_t x_pitch, int nx, const float* h_tap
         k_state_update<<<grid, 128, 0, st>>>(d_x, x_pitch, nx, d_state, nstate);
     }
     CU(cudaGetLastError());
-    CU(cudaFreeAsync(d_h, st));
+    if (owned) CU(cudaFreeAsync(d_h, st));
     return SDRB_OK;
 }
 
