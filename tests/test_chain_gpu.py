@@ -345,6 +345,30 @@ def test_pll_cta_sizes(capi, oracle, station_iq, monkeypatch, cap, S):
         _assert_same(got[s], wants[s % 3], ["pcm"] + RDS_KEYS, f"cap {cap} stream {s}")
 
 
+@pytest.mark.parametrize("setting", ["0", "1", None])
+def test_sm_partition_is_optional_and_changes_nothing(capi, oracle, station_iq, monkeypatch, setting):
+    """The overlap-mode streams live in two green contexts (PLL: 32 SMs, FIR: the rest) unless the driver refuses, the
+    batch is FIR-bound (more than 1024 stereo+RDS stations) or SDRB_SM_PARTITION=0: the results are the oracle's either way."""
+    if setting is None:
+        monkeypatch.delenv("SDRB_SM_PARTITION", raising=False)
+    else:
+        monkeypatch.setenv("SDRB_SM_PARTITION", setting)
+    with capi.Chain(0, "r", n_streams=5) as ch:
+        part = ch.sm_partition()
+    if setting == "0":
+        assert part == (0, 0)
+    else:
+        assert part == (0, 0) or (part[0] >= 32 and part[1] > 0 and part[0] + part[1] <= 148), part
+    with capi.Chain(0, "r", n_streams=1100) as ch:  # 70 PLL warps: the FIR kernels bound the step, no partition by default
+        assert setting == "1" or ch.sm_partition() == (0, 0)
+    nblocks = 8
+    iqs = [station_iq(k % 3, 0, nblocks) for k in range(5)]
+    got = run_cuda_chain(capi, 0, "r", iqs, nblocks, overlap=True)
+    wants = {k: oracle.chain(0, "r", station_iq(k, 0, nblocks)) for k in range(3)}
+    for s in range(5):
+        _assert_same(got[s], wants[s % 3], ["pcm"] + RDS_KEYS, f"partition {setting} stream {s}")
+
+
 @pytest.mark.parametrize("mode", [1, 2, 3])
 def test_type_r_outside_mode0_is_the_stereo_chain_with_gated_records(capi, oracle, station_iq, mode):
     """`project <1|2|3> r` in the reference plays stereo audio and its RDS thread prints nothing
