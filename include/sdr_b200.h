@@ -179,7 +179,8 @@ typedef struct {
 } sdrb_chain_info;
 
 /* Tuning knob read here: the environment variable SDRB_PLL_MAX_CTAS (1..148) overrides the number of SMs the PLL
- * kernel may occupy (default: 64 up to 1024 stereo+RDS stations, 32 beyond; results do not depend on it). */
+ * kernel may occupy (default: 32; results do not depend on it), SDRB_SM_PARTITION=0|1 switches the green-context SM
+ * partition of the overlap-mode streams off | on (default: on up to 1024 stereo+RDS stations, see sdrb_chain_sm_partition). */
 int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out);
 int sdrb_chain_destroy(sdrb_chain* c);
 int sdrb_chain_get_info(const sdrb_chain* c, sdrb_chain_info* info);

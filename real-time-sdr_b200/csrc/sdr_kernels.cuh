@@ -564,9 +564,10 @@ struct PllArgs {
     int n_streams;
 };
 
-// CTA size of k_pll: one warp per SM measures fastest (about 5 % fewer cycles per sample than four warps, one per
-// sub-partition: the warps of one SM still share its instruction and constant caches), so the launch uses the
-// smallest size that keeps the PLL on at most kPllMaxCtas SMs and leaves the rest to the FIR kernels.
+// CTA size of k_pll: the launch uses the smallest CTA that keeps the PLL on at most `pll_max_ctas` SMs (sdr_chain.cu:
+// 32 by default, i.e. two warps per SM at 1024 stereo+RDS stations) and leaves the rest to the FIR kernels.  Alone, one
+// warp per SM is 1 % faster than two and 4 % faster than four (the warps of an SM share its instruction and constant
+// caches), but the 32 SMs that costs the FIR side are worth more (profiles/README.md).  kPllMaxCtas bounds the knob.
 constexpr int kPllThreads = 128;  // largest CTA; also the block size of the generic single-call kernel
 constexpr int kPllMaxCtas = 64;
 
