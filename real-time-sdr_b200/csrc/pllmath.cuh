@@ -19,6 +19,16 @@
 #include <string.h>
 
 #define SDRB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+// Code that runs about once per 10^5 samples: out of line on the device, so that it is neither duplicated at every call
+// site nor interleaved with the lines the careful path does execute.  (The careful repeat of k_pll runs cold: what it
+// costs is instruction-cache misses, ~20 000 cycles per repeat measured, not arithmetic.)
+#if defined(__CUDA_ARCH__)
+#define SDRB_COLD __device__ __noinline__
+#elif defined(__CUDACC__)
+#define SDRB_COLD __host__ __device__ inline
+#else
+#define SDRB_COLD inline
+#endif
 #if defined(__CUDACC__)
 #define SDRB_HD __host__ __device__ __forceinline__
 #else
@@ -344,7 +354,7 @@ SDRB_HD void sincos_fast(double x, double& s, double& c, bool& tiny) {
 
 // slow tier: the same k, the reduction carried in double-double with pi/2 to ~170 bits, Taylor series
 // in double-double.  Returns RN_double(sin x), RN_double(cos x) up to ~2^-100.
-SDRB_HD void sincos_slow(double x, double& s, double& c) {
+SDRB_COLD void sincos_slow(double x, double& s, double& c) {
     double kd = rint(dmul(x, kTwoOverPi));
     double r2 = dfma(-kd, kP2, dfma(-kd, kP1, x));  // exact: x - k P1 has at most log2|k| + 1 significant bits, then k P2 lines up
     dd r = dd_add(dd{r2, 0.0}, dd_neg(two_prod(kd, kP3)));  // exact products (53 bits only hold them for |k| < 2^31)
@@ -449,7 +459,7 @@ SDRB_HD double atan2_fast(double ax, double ay, bool xneg, const AtanTab& tab) {
     return res;
 }
 
-SDRB_HD double atan2_slow(double ax, double ay, bool xneg, const AtanTab& tab) {
+SDRB_COLD double atan2_slow(double ax, double ay, bool xneg, const AtanTab& tab) {
     bool swap = ay > ax;
     AtanRed rd = atan_reduce(swap ? ax : ay, swap ? ay : ax);
     dd z = dd_div(dd{rd.nn, 0.0}, dd{rd.dn, 0.0});
@@ -922,7 +932,8 @@ SDRB_HD float pll_step_spec(float in, double rin, PllFast& f, const PllCoef& k, 
 // The tests are leaner than pll_step_spec's (same guarantees, fewer instructions beside the chain):
 //   e   : RN_f(e - 2^-43) == RN_f(e + 2^-43), i.e. no float rounding step within the error bound of e, whatever its
 //         binade; replaces the exponent-dependent window of ambig_abs (and rejects |e| < ~2^-19 by itself);
-//   sa,cr : low 29 bits within 512 of the tie pattern (the lean kernels are good to 2^-46.6), as one add and one masked compare;
+//   sa,cr : low 29 bits within 512 (sa: the lean sine is good to 2^-46.3) / 64 (cr: 2^-50) of the tie pattern, as one add and one
+//           masked compare;
 //   td  : exponent field against the one stored with the magic constant (one masked compare);
 //   in  : the range test is made once per chunk on min / max of the four inputs (pll_chunk4r).
 struct PllHead {
@@ -930,8 +941,10 @@ struct PllHead {
     uint32_t Ke, bh;  // bh: high word of base (for the +-2 test)
 };
 constexpr double kAtanTol = 0x1p-43;  // 2^kAtanTolLog2
-SDRB_HD unsigned ambig_tie29(double v) {  // low 29 bits in [tie - 512, tie + 511]: within 2^-44 relative of a float rounding tie
-    return (unsigned)((((dlo(v) + 2u * kAmbigUlps) & 0x1FFFFC00u) ^ 0x10000000u) == 0u);
+// low 29 bits in [tie - W, tie + W - 1], W a power of two: within W double-ulps of a float rounding tie
+template <uint32_t W>
+SDRB_HD unsigned ambig_tie29(double v) {
+    return (unsigned)((((dlo(v) + W) & (0x1FFFFFFFu & ~(2u * W - 1u))) ^ 0x10000000u) == 0u);
 }
 SDRB_HD PllHead pll_spec_head(float in, double rin, const PllFast& f, const PllK& kk) {
     const uint32_t rhi = dhi(f.r);
@@ -955,9 +968,21 @@ SDRB_HD PllHead pll_spec_head(float in, double rin, const PllFast& f, const PllK
 // The tests of a head: sa / cr are the values it was computed from (their float roundings fa, fc must not be near a tie);
 // wrap (|e| < pi; NaN / inf from an unusable input land here too), float rounding of e, base at +-2.
 SDRB_HD void pll_spec_head_tests(const PllHead& h, double sa, double cr_, unsigned& bad) {
-    const uint32_t elo = d2f_known(dadd(h.e, -kAtanTol), h.Ke), ehi = d2f_known(dadd(h.e, kAtanTol), h.Ke);
+    // Error bound of e.  Every term of it scales with sa cr = |sin 2r| / 2: the linearisation and the reciprocal (2^-22.5 +
+    // 2^-23 relative to a perturbation of at most 2^-22 sa cr), the kernels' 2^-46.3, the double roundings of products of
+    // size sa cr: together below 2^-43.3 sa cr; the only absolute term is the rounding of base (<= 2^-51, zero in the
+    // quadrant where e = -r + ...).  Tolerance: 2^-42 sa + 2^-50 (one fma; 2.4x the bound).  With the flat 2^-43 of round 1
+    // every binade of small |e| rejected as often as the top one (the float grid of e shrinks with |e|, the tolerance did
+    // not): 2.5e-5 rejections per sample, four fifths of them below |e| = 1/4 and avoidable, each a careful repeat that
+    // stalls the whole warp for thousands of cycles.
+#if defined(SDRB_PLL_FLAT_TOL)
+    const double tol = kAtanTol;
+#else
+    const double tol = dfma(sa, 0x1p-42, 0x1p-50);
+#endif
+    const uint32_t elo = d2f_known(dadd(h.e, -tol), h.Ke), ehi = d2f_known(dadd(h.e, tol), h.Ke);
     bad |= SDRB_BAD((dhi(h.e) & 0x7FFFFFFFu) >= 0x400921F9u, 1) | SDRB_BAD(elo != ehi, 2) |
-           SDRB_BAD(((h.bh & 0x7FFFFFFFu) - 0x3FFFFFFFu) <= 1u, 3) | SDRB_BAD(ambig_tie29(sa), 6) | SDRB_BAD(ambig_tie29(cr_), 7);
+           SDRB_BAD(((h.bh & 0x7FFFFFFFu) - 0x3FFFFFFFu) <= 1u, 3) | SDRB_BAD(ambig_tie29<512>(sa), 6) | SDRB_BAD(ambig_tie29<64>(cr_), 7);
 }
 SDRB_HD float pll_spec_tail(const PllHead& h, PllFast& f, const PllCoef& k, const PllK& kk, unsigned& bad) {
     const float errorD = bitsf(d2f_known(h.e, h.Ke));
@@ -994,13 +1019,25 @@ SDRB_HD void pll_fast_resync(PllFast& f, const PllCoef& k) {
 #define SDRB_RARE inline
 #endif
 // the careful repeat of four steps (rare: kept out of line on the device so the hot loop stays small)
+// one careful step, out of line: the four steps of a repeat run through the same instruction-cache lines
+SDRB_RARE float pll_step_fast_cold(float in, double rin, PllFast& f, const PllCoef& k, const AtanTab& tab) {
+    return pll_step_fast(in, rin, f, k, tab);
+}
+// The repeat of four steps after a raised flag, on the careful path: a loop over one out-of-line step, so that the four
+// steps run through the same instruction-cache lines.  (Trying each step on the speculative path first and sending only the
+// one that fails to the careful step was built too: ptxas then no longer proves the warp converged at the loop's vote and
+// guards it with a BRA.DIV, which cost 27 cycles per sample.)
 SDRB_RARE void pll_redo4(float i0, float i1, float i2, float i3, double r0, double r1, double r2, double r3, PllFast& f,
                          const PllCoef& k, const AtanTab& tab, float& t0, float& t1, float& t2, float& t3) {
     if (!f.generic_next) pll_fast_resync(f, k);  // sa / cr may be untested (rotated loop): derive the state again from the float phase
-    t0 = pll_step_fast(i0, pll_guard_recip(i0, r0), f, k, tab);  // r0..r3 are raw reciprocals: guarded here
-    t1 = pll_step_fast(i1, pll_guard_recip(i1, r1), f, k, tab);
-    t2 = pll_step_fast(i2, pll_guard_recip(i2, r2), f, k, tab);
-    t3 = pll_step_fast(i3, pll_guard_recip(i3, r3), f, k, tab);
+    const float in[4] = {i0, i1, i2, i3};
+    const double rr[4] = {r0, r1, r2, r3};  // raw reciprocals: guarded here
+    float t[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < 4; j++) t[j] = pll_step_fast_cold(in[j], pll_guard_recip(in[j], rr[j]), f, k, tab);
+    t0 = t[0]; t1 = t[1]; t2 = t[2]; t3 = t[3];
 }
 
 // Four consecutive samples: speculative run, verified once; the careful path only on failure.

@@ -616,6 +616,10 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
     const PllLoop& lp = a.loop[blockIdx.y];
     const int s = blockIdx.x * THREADS + threadIdx.x;
     if (s >= a.n_streams) return;
+#if defined(SDRB_PLL_TIMESTAMPS)
+    unsigned long long ts0 = 0;
+    if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts0));
+#endif
     PllStateDev sd = lp.st[s];
     cr::PllState st{sd.feedbackI, sd.feedbackQ, sd.integrator, sd.phaseEst, sd.trigOffset};
     const cr::PllCoef k = lp.coef;
@@ -756,6 +760,15 @@ __global__ void __launch_bounds__(THREADS) k_pll(const PllArgs a) {
     for (int b = 1; b <= lp.trig.halo && b <= a.n; b++) nh[-b] = out[a.n - b];
     cr::pll_fast_store(f, st);
     lp.st[s] = PllStateDev{st.feedbackI, st.feedbackQ, st.integrator, st.phaseEst, st.trigOffset};
+#if defined(SDRB_PLL_TIMESTAMPS)
+    if (threadIdx.x == 0) {
+        unsigned long long ts1;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("PLLTS %llu %llu %d %d %u\n", ts0, ts1, (int)blockIdx.x, (int)blockIdx.y, smid);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
