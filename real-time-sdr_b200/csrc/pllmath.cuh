@@ -970,15 +970,17 @@ SDRB_HD PllHead pll_spec_head(float in, double rin, const PllFast& f, const PllK
 SDRB_HD void pll_spec_head_tests(const PllHead& h, double sa, double cr_, unsigned& bad) {
     // Error bound of e.  Every term of it scales with sa cr = |sin 2r| / 2: the linearisation and the reciprocal (2^-22.5 +
     // 2^-23 relative to a perturbation of at most 2^-22 sa cr), the kernels' 2^-46.3, the double roundings of products of
-    // size sa cr: together below 2^-43.3 sa cr; the only absolute term is the rounding of base (<= 2^-51, zero in the
-    // quadrant where e = -r + ...).  Tolerance: 2^-42 sa + 2^-50 (one fma; 2.4x the bound).  With the flat 2^-43 of round 1
+    // size sa cr: together below 2^-43.3 sa cr; the only absolute terms are the four double roundings of base and e at a
+    // magnitude of up to pi (<= 2^-50 together; zero in the quadrant where e = -r + ...).  Tolerance: 2^-42 sa + 2^-48 (one
+    // fma; 2.4x / 4x those bounds; tests/test_pllmath.py measures the error against long-double atan2: it stays below
+    // a quarter of the tolerance on 10M random states).  With the flat 2^-43 of round 1
     // every binade of small |e| rejected as often as the top one (the float grid of e shrinks with |e|, the tolerance did
     // not): 2.5e-5 rejections per sample, four fifths of them below |e| = 1/4 and avoidable, each a careful repeat that
     // stalls the whole warp for thousands of cycles.
 #if defined(SDRB_PLL_FLAT_TOL)
     const double tol = kAtanTol;
 #else
-    const double tol = dfma(sa, 0x1p-42, 0x1p-50);
+    const double tol = dfma(sa, 0x1p-42, 0x1p-48);
 #endif
     const uint32_t elo = d2f_known(dadd(h.e, -tol), h.Ke), ehi = d2f_known(dadd(h.e, tol), h.Ke);
     bad |= SDRB_BAD((dhi(h.e) & 0x7FFFFFFFu) >= 0x400921F9u, 1) | SDRB_BAD(elo != ehi, 2) |

@@ -25,6 +25,28 @@ void crh_poly_lean(const double* r, int n, double* s, double* c) {
     pll_k_load_lean(kk);
     for (int i = 0; i < n; i++) sincos_poly2_lean(r[i], fabs(r[i]), s[i], c[i], kk);
 }
+// Error of the speculative phase detector against atan2 in long double, in units of the tolerance its acceptance test
+// grants it (2^-42 sa + 2^-48): out[0] = max ratio, out[1] = samples used, out[2] = max |e - ref|.
+void crh_head_error(const float* theta, const float* in, int n, double* out) {
+    PllK kk;
+    pll_k_load_lean(kk);
+    double worst = 0, worst_abs = 0, used = 0;
+    for (int i = 0; i < n; i++) {
+        PllFast f{};
+        pll_fast_sincos(theta[i], f);
+        if (f.generic_next || in[i] == 0.0f) continue;
+        const PllHead h = pll_spec_head(in[i], 1.0 / fabs((double)in[i]), f, kk);
+        if (!(fabs(h.e) < 3.14159)) continue;  // the wrap test sends these to the careful path
+        const float eI = fmul(in[i], f.fbI), eQ = fmul(in[i], -f.fbQ);
+        const long double ref = atan2l((long double)eQ, (long double)eI);
+        const double err = (double)fabsl((long double)h.e - ref);
+        const double tol = f.sa * 0x1p-42 + 0x1p-48;
+        if (err / tol > worst) worst = err / tol;
+        if (err > worst_abs) worst_abs = err;
+        used += 1;
+    }
+    out[0] = worst; out[1] = used; out[2] = worst_abs;
+}
 void crh_sincos(const float* t, int n, float* s, float* c) { for (int i = 0; i < n; i++) sincos_f(t[i], s[i], c[i]); }
 void crh_cos(const float* t, int n, float* c) { for (int i = 0; i < n; i++) c[i] = cos_f(t[i]); }
 void crh_cos_lean(const float* t, int n, float* c) { for (int i = 0; i < n; i++) c[i] = cos_lean_f(t[i]); }

@@ -246,3 +246,26 @@ def test_lean_kernels_error_bound(host):
         worst_c = max(worst_c, abs((mp.mpf(float(ci)) - mp.cos(x)) / mp.cos(x)))
     assert worst_s < mp.mpf(2) ** -46.3, float(mp.log(worst_s, 2))
     assert worst_c < mp.mpf(2) ** -50, float(mp.log(worst_c, 2))  # approximation 2^-51.5 plus the rounding of the evaluation
+
+
+def test_phase_detector_error_stays_inside_its_tolerance(host):
+    """The speculative step accepts errorD = RN_f(e) when no float rounding tie lies within 2^-42 sa + 2^-48 of e.  That is
+    only sound if |e - atan2(errorQ, errorI)| stays below that tolerance: measured here against long-double atan2 on 4M
+    random (NCO phase, input) pairs, small reduced arguments (where the tolerance shrinks with sa) included."""
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    host.crh_head_error.argtypes = [f32p, f32p, C.c_int, f64p]
+    rng = np.random.default_rng(11)
+    n = 1_000_000
+    k = rng.integers(0, 4000, n)
+    thetas = [
+        (rng.random(n) * 6e6).astype(np.float32),                                                   # anywhere
+        (k * (np.pi / 2) + rng.standard_normal(n) * 1e-3).astype(np.float32),                        # near multiples of pi/2: small sa
+        (k * (np.pi / 2) + 10.0 ** rng.uniform(-7, -1, n) * rng.choice([-1, 1], n)).astype(np.float32),
+        (rng.random(n) * 3e9).astype(np.float32),                                                   # coarse float grid
+    ]
+    for th in thetas:
+        x = (rng.standard_normal(n) * 10.0 ** rng.uniform(-3, 1, n)).astype(np.float32)
+        out = np.zeros(3)
+        host.crh_head_error(np.ascontiguousarray(th), x, n, out)
+        assert out[1] > 0.5 * n
+        assert out[0] < 0.4, f"error reaches {out[0]:.2f} of the tolerance (max abs {out[2]:.3e})"
