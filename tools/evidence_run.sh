@@ -4,7 +4,7 @@
 tag=${1:-x}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_${tag}.log 2>&1; tail -2 gpurun_out/pytest_gpu_${tag}.log
+[ -n "${SKIP_TESTS:-}" ] || { python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_${tag}.log 2>&1; tail -2 gpurun_out/pytest_gpu_${tag}.log; }
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${tag}.log 2>&1; tail -1 gpurun_out/smoke_${tag}.log
 timeout 900 python bench.py > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${tag}_reference_arm.json 2> gpurun_out/bench_${tag}_reference_arm.err
