@@ -99,8 +99,8 @@ struct sdrb_chain {
     float* d_audio_pm = nullptr;   // phase-major audio taps (up > 1)
     float* d_audio_tm = nullptr;   // thread-major audio taps of the phase-class resampler (k_audio_updown_pc), nullptr: not applicable
     int* d_audio_res = nullptr;    // output residue per thread of that kernel
-    float* d_rds_perm = nullptr;   // permuted RDS low-pass taps
-    int* d_rds_thread_phase = nullptr;
+    float2* d_rds_res_taps = nullptr;  // RDS low-pass taps as the resampler lanes read them, [kResIter][kResLanes]
+    int4* d_rds_res_lane = nullptr;    // [kResLanes] the lanes (ResLane, sdr_kernels.cuh)
     // input
     uint8_t* d_iq[2] = {nullptr, nullptr};  // staging for process_host
     size_t iq_pitch = 0;
@@ -310,7 +310,7 @@ cudaError_t copy_rows_h2d(sdrb_chain* c, uint8_t* dst, const uint8_t* h_iq, size
 size_t rds_backend_smem(int n_if, int n_out) {
     const int rrc_tiles = (n_out + kRrcTile - 1) / kRrcTile;
     const size_t nfilt = (size_t)rrc_tiles * kRrcTile + kState;
-    return sizeof(float) * (round_up((size_t)n_if + kState, 4) + nfilt + nfilt / kRrcR + 8);
+    return sizeof(float) * ((size_t)rds_sdc_len(n_if) + nfilt + nfilt / kRrcR + 8);
 }
 
 // Makes the caller-visible stream wait for everything issued on the internal streams (no host blocking).
@@ -497,8 +497,8 @@ int process_block_impl(sdrb_chain* c, const uint8_t* d_iq, size_t iq_pitch, cuda
         RdsArgs a{};
         a.dc = c->rdc.cur(b); a.dc_pitch = c->rdc.pitch;
         a.n_in = n_if; a.n_out = c->info.rds_block; a.sps = 39; a.rds_on = c->cfg.rds_on;
-        a.taps_perm = c->d_rds_perm;
-        a.thread_phase = c->d_rds_thread_phase;
+        a.res_taps = c->d_rds_res_taps;
+        a.res_lane = c->d_rds_res_lane;
         a.rrc = c->rrc_h;
         a.filt_state_in = c->d_filt_state[b & 1];
         a.filt_state_out = c->d_filt_state[(b + 1) & 1];
@@ -746,25 +746,15 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         const int nh = kTaps * kRdsUp;
         std::vector<float> lh(nh);
         TRY(sdrb_design_lpf_gain((float)(cfg->if_Fs * kRdsUp), 3e3f, nh, kRdsUp, lh.data()));  // src/rds.cpp:61
-        // thread -> output residue: warp by warp, 32 residues whose input offsets floor(640 tp/247) differ modulo 32
-        std::vector<int> thread_phase(256, -1);
-        {
-            std::vector<std::vector<int>> by_bank(32);
-            for (int tp = 0; tp < kRdsUp; tp++) by_bank[((kRdsDown * tp) / kRdsUp) % 32].push_back(tp);
-            for (int b = 0; b < 32; b++)
-                for (size_t i = 0; i < by_bank[b].size(); i++) thread_phase[32 * i + b] = by_bank[b][i];  // at most 8 per bank
-        }
-        std::vector<float> perm((size_t)kTaps * 256, 0.0f);
-        for (int th = 0; th < 256; th++) {
-            const int tp = thread_phase[th];
-            if (tp < 0) continue;
-            const int phase = (kRdsDown * tp) % kRdsUp;
-            for (int j = 0; j < kTaps; j++) perm[(size_t)j * 256 + th] = lh[phase + kRdsUp * j];
-        }
-        TRY(dalloc(c, (void**)&c->d_rds_perm, perm.size() * sizeof(float)));
-        TRY(dalloc(c, (void**)&c->d_rds_thread_phase, 256 * sizeof(int)));
-        TRYCU(cudaMemcpyAsync(c->d_rds_perm, perm.data(), perm.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-        TRYCU(cudaMemcpyAsync(c->d_rds_thread_phase, thread_phase.data(), 256 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        // resampler lanes and their tap table (res_lanes.h)
+        static_assert(sizeof(ResLane) == sizeof(int4) && sizeof(float2) == 2 * sizeof(float), "uploaded as int4 / float2");
+        std::vector<ResLane> lanes(kResLanes);
+        std::vector<float> rtaps((size_t)kResIter * kResLanes * 2);
+        if (build_res_lanes(lh.data(), lanes.data(), rtaps.data()) < 0) { sdrb_chain_destroy(c); return fail(SDRB_ERR_INVALID, "resampler lanes: no free lane"); }
+        TRY(dalloc(c, (void**)&c->d_rds_res_taps, rtaps.size() * sizeof(float)));
+        TRY(dalloc(c, (void**)&c->d_rds_res_lane, lanes.size() * sizeof(ResLane)));
+        TRYCU(cudaMemcpyAsync(c->d_rds_res_taps, rtaps.data(), rtaps.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        TRYCU(cudaMemcpyAsync(c->d_rds_res_lane, lanes.data(), lanes.size() * sizeof(ResLane), cudaMemcpyHostToDevice, c->stream));
         TRYCU(cudaStreamSynchronize(c->stream));
     }
 

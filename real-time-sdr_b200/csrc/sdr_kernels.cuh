@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "pllmath.cuh"
+#include "res_lanes.h"
 
 namespace sdrb {
 
@@ -1075,7 +1076,6 @@ __global__ void __launch_bounds__(kUpdThreads) k_audio_updown_pc(const AudioArgs
 // Manchester and differential decode, and (every 15 decode blocks) frame sync.
 // /root/reference/src/rds.cpp:130-189, src/rds_utilities.cpp:4-88,313-400.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRdsUp = 247, kRdsDown = 640;
 constexpr int kRdsThreads = 256;
 constexpr int kRdsMaxBits = 48;
 constexpr int kRdsMaxGroups = 8;
@@ -1107,8 +1107,8 @@ struct RdsArgs {
     int n_out;             // n_in*247/640
     int sps;
     int rds_on;
-    const float* taps_perm;  // [kTaps][256]: taps_perm[j*256 + thread] = h_lpf[(640*tp % 247) + 247*j], tp = thread_phase[thread]
-    const int* thread_phase; // [256]: the output residue tp (n = tp mod 247) each thread owns, -1 = idle
+    const float2* res_taps;  // [kResIter][128]: the two branch taps of resampler lane `tl` at loop step j (see ResLane)
+    const int4* res_lane;    // [128] ResLane as int4
     Taps101 rrc;
     float* filt_state_in;    // [n_streams][kState] last rds_filt samples of the previous block
     float* filt_state_out;
@@ -1145,7 +1145,13 @@ __device__ __forceinline__ uint32_t bitbuf_window26(const uint32_t* buf, int idx
 
 constexpr int kRrcR = 12;
 constexpr int kRrcTile = kRrcR * kRdsThreads;  // 3072 outputs per pass
-constexpr int kResQ = 12;                      // resampler outputs per thread: ceil(2836 / 247); the kernel requires n_out <= 12 * 247
+static_assert(kResTaps == kTaps, "res_lanes.h");  // resampler lanes, loop steps and lags: res_lanes.h
+// floats of the staged input: the block with its carried state, or (longer) what the loads of a lane may touch: outputs
+// that do not exist (q = 11 for most residues) are computed on whatever lies there and never stored
+__host__ __device__ constexpr int rds_sdc_len(int n_in) {
+    const int need = kState + kRdsDown * kResQ + kResLagMax + 1, have = n_in + kState;
+    return ((need > have ? need : have) + 3) / 4 * 4;
+}
 
 
 __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_constant__ RdsArgs a) {
@@ -1156,7 +1162,7 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     const int rrc_tiles = (n_out + kRrcTile - 1) / kRrcTile;
     const int nfilt_pad = rrc_tiles * kRrcTile + kState;
     float* sdc = smem;                                // [n_in + kState]; later reused as sclean [n_out]
-    float* sfilt = smem + (n_in + kState + 3) / 4 * 4;  // padded layout, pad_pos<kRrcR>
+    float* sfilt = smem + rds_sdc_len(n_in);            // padded layout, pad_pos<kRrcR>
     __shared__ int ssum[64];
     __shared__ int ssym[160];
     __shared__ int8_t stype[kBitBufWords * 32];
@@ -1170,46 +1176,98 @@ __global__ void __launch_bounds__(kRdsThreads) k_rds_backend(const __grid_consta
     const int start_in = st->start, half_in = st->half_symbol, last_in = st->last_bit;
     const int nbits_in = st->nbits, decoder_cont_in = st->decoder_cont;
 
-    // ---- stage rds_dc (with the carried 100-sample state in front)
+    // ---- stage rds_dc (with the carried 100-sample state in front): one bulk copy (TMA) issued by thread 0 when the row is
+    // 16-byte aligned (it is for the chain's own rings), the few floats behind the last multiple of 16 bytes by plain loads
+    static_assert(kRdsThreads == 2 * kResLanes, "two threads per resampler lane");
+    __shared__ __align__(8) unsigned long long bar;
     const float* dc = a.dc + (size_t)s * a.dc_pitch - kState;
-    for (int u = t; u < n_in + kState; u += kRdsThreads) sdc[u] = dc[u];
+    const int n_stage = n_in + kState;
+#if defined(SDRB_RDS_NO_TMA)  // measurement variant: plain loads only
+    const int n_bulk = 0;
+#else
+    const int n_bulk = ((reinterpret_cast<uintptr_t>(dc) & 15u) == 0) ? (n_stage & ~3) : 0;
+#endif
+    if (n_bulk) {
+        if (t == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (t == 0) {
+            mbar_expect_tx(&bar, (uint32_t)n_bulk * 4u);
+            tma_load_1d(sdc, dc, (uint32_t)n_bulk * 4u, &bar);
+        }
+    }
+    for (int u = n_bulk + t; u < n_stage; u += kRdsThreads) sdc[u] = dc[u];
     for (int u = t; u < kState; u += kRdsThreads)
         sfilt[pad_pos<kRrcR>(u)] = a.filt_state_in[(size_t)s * kState + u];
     for (int u = n_out + kState + t; u < nfilt_pad; u += kRdsThreads) sfilt[pad_pos<kRrcR>(u)] = 0.0f;
     if (t < 64) ssum[t] = 0;
+    if (n_bulk) mbar_wait(&bar, 0);
     __syncthreads();
 
     // ---- 247/640 resampler (/root/reference/src/filter.cpp:123-147, src/rds.cpp:130).
-    // Outputs n and n+247 share the polyphase branch, so one thread owns n = tp + 247 q, q = 0..11, and streams its 101
-    // branch taps h[phase + 247 j] once; outputs 2p and 2p+1 share one packed accumulator (FFMA2 + FADD2: half the
-    // floating-point instructions of the scalar form, so the one shared-memory load per MAC has issue slots to go into).
-    // Which tp a thread owns is a host-made permutation (thread_phase): the 32 lanes of a warp get input offsets
-    // floor(640 tp / 247) that are distinct modulo 32, so those loads are bank-conflict free.
-    const int tp = a.thread_phase[t];
-    if (tp >= 0) {
-        const float* xb = sdc + (kRdsDown * tp) / kRdsUp + kState;  // x[(n*down - phase)/up] for q = 0
-        float2 acc[kResQ / 2];
+    // Outputs n and n + 247 share the polyphase branch (taps h[phase + 247 j]) and adjacent residues share the input
+    // (see ResLane above): a thread owns two residues x six outputs n = tp + 247 q, loads per loop step one sample per q
+    // and one float2 of taps, and does twelve MACs with them, outputs 2p and 2p+1 of a residue in one packed accumulator
+    // (FFMA2 + FADD2).  Round 2 started from one residue per thread (one shared-memory load per MAC: the kernel was bound
+    // by the load/store unit at twice the time of its floating-point work).
+    {
+        const int tl = t & (kResLanes - 1), qh = t / kResLanes;
+        const int4 ln = a.res_lane[tl];  // x tp_hi (-1: idle lane), y tp_lo (-1: none), z base, w lag_hi | lag_lo << 8
+        if (ln.x >= 0 && qh < 2) {
+            constexpr int HQ = kResQ / 2;       // outputs per residue and thread
+            const int lag_hi = ln.w & 0xFF, lag_lo = (ln.w >> 8) & 0xFF;
+            const bool has_lo = ln.y >= 0;
+            const float* xb = sdc + kState + ln.z + kRdsDown * HQ * qh;  // x[base + 640 q - j] for the thread's first q at j = 0
+            const float2* tab = a.res_taps + tl;
+            float2 aH[HQ / 2], aL[HQ / 2];
 #pragma unroll
-        for (int pq = 0; pq < kResQ / 2; pq++) acc[pq] = make_float2(0.0f, 0.0f);
-        const bool last_valid = (kResQ - 1) * kRdsUp + tp < n_out;  // output 11 exists for tp < 119 only: its inputs must not be read beyond the block
-#pragma unroll 8  // eight tap loads in flight ahead of their MACs
-        for (int j = 0; j < kTaps; j++) {
-            const float hj = __ldg(a.taps_perm + j * 256 + t);
+            for (int p = 0; p < HQ / 2; p++) aH[p] = aL[p] = make_float2(0.0f, 0.0f);
 #pragma unroll
-            for (int pq = 0; pq < kResQ / 2; pq++) {
-                const float x0 = xb[2 * kRdsDown * pq - j];
-                const float x1 = (pq == kResQ / 2 - 1 && !last_valid) ? 0.0f : xb[2 * kRdsDown * pq + kRdsDown - j];
-                acc[pq] = mac(acc[pq], hj, make_float2(x0, x1));
+            for (int j = 0; j < kResLagMax; j++) {  // first steps: a residue joins at its lag
+                const float2 h = __ldg(tab + j * kResLanes);
+                const bool vH = j >= lag_hi, vL = has_lo && j >= lag_lo;
+#pragma unroll
+                for (int p = 0; p < HQ / 2; p++) {
+                    const float2 x = make_float2(xb[2 * kRdsDown * p - j], xb[2 * kRdsDown * p + kRdsDown - j]);
+                    if (vH) aH[p] = mac(aH[p], h.x, x);
+                    if (vL) aL[p] = mac(aL[p], h.y, x);
+                }
             }
-        }
+#pragma unroll 7  // 98 uniform steps; seven tap loads in flight ahead of their MACs
+            for (int j = kResLagMax; j < kTaps; j++) {
+                const float2 h = __ldg(tab + j * kResLanes);
 #pragma unroll
-        for (int qq = 0; qq < kResQ; qq++) {
-            const int n = qq * kRdsUp + tp;
-            const float y = (qq & 1) ? acc[qq / 2].y : acc[qq / 2].x;
-            if (n < n_out) {
-                sfilt[pad_pos<kRrcR>(n + kState)] = y;
-                if (a.filt_out) a.filt_out[(size_t)s * n_out + n] = y;
-                if (n >= n_out - kState) a.filt_state_out[(size_t)s * kState + (n - (n_out - kState))] = y;
+                for (int p = 0; p < HQ / 2; p++) {
+                    const float2 x = make_float2(xb[2 * kRdsDown * p - j], xb[2 * kRdsDown * p + kRdsDown - j]);
+                    aH[p] = mac(aH[p], h.x, x);
+                    aL[p] = mac(aL[p], h.y, x);  // (a lane without a partner has zero taps here and never stores the result)
+                }
+            }
+#pragma unroll
+            for (int j = kTaps; j < kResIter; j++) {  // last steps: a residue leaves after its 101st tap
+                const float2 h = __ldg(tab + j * kResLanes);
+                const bool vH = j < kTaps + lag_hi, vL = has_lo && j < kTaps + lag_lo;
+#pragma unroll
+                for (int p = 0; p < HQ / 2; p++) {
+                    const float2 x = make_float2(xb[2 * kRdsDown * p - j], xb[2 * kRdsDown * p + kRdsDown - j]);
+                    if (vH) aH[p] = mac(aH[p], h.x, x);
+                    if (vL) aL[p] = mac(aL[p], h.y, x);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int tp = r ? ln.y : ln.x;
+                if (tp < 0) continue;
+#pragma unroll
+                for (int qq = 0; qq < HQ; qq++) {
+                    const int n = (HQ * qh + qq) * kRdsUp + tp;
+                    const float2 v = r ? aL[qq / 2] : aH[qq / 2];
+                    const float y = (qq & 1) ? v.y : v.x;
+                    if (n < n_out) {
+                        sfilt[pad_pos<kRrcR>(n + kState)] = y;
+                        if (a.filt_out) a.filt_out[(size_t)s * n_out + n] = y;
+                        if (n >= n_out - kState) a.filt_state_out[(size_t)s * kState + (n - (n_out - kState))] = y;
+                    }
+                }
             }
         }
     }

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../real-time-sdr_b200/csrc/pllmath.cuh"
+#include "../../real-time-sdr_b200/csrc/res_lanes.h"
 
 using namespace sdrb::cr;
 static const AtanTab kTab = SDRB_ATAN_TAB_INIT;
@@ -193,5 +194,63 @@ void crh_pll_fast(const float* in, int n, float freq, float Fs, float scale, flo
     pll_fast_store(f, st);
     st4[0] = st.feedbackI; st4[1] = st.feedbackQ; st4[2] = st.integrator; st4[3] = st.phaseEst; *trig = st.trigOffset;
     if (stats) { stats[0] += gen_atan; stats[1] += gen_sc; }
+}
+
+// The 247/640 RDS resampler of k_rds_backend replayed on the host: the lane tables of res_lanes.h (the same function the
+// chain uploads) and the kernel's per-thread loop, statement by statement (real-time-sdr_b200/csrc/sdr_kernels.cuh).
+// x: [100 + n_in] the carried state followed by the block; every float the kernel may load beyond that is NaN here, so a
+// load that must not matter shows up if it does.  y: [n_out].  info[0] = pairs without a conflict-free lane, info[1] = the
+// largest number of lanes of one warp whose loads fall into the same bank, info[2] = outputs written more than once,
+// info[3] = outputs never written.  Returns 0, or -1 if the lanes ran out.
+int crh_resampler_lanes(const float* lh, const float* x, int n_in, int n_out, float* y, int* info) {
+    using namespace sdrb;
+    constexpr int kState = kResTaps - 1;
+    std::vector<ResLane> lanes(kResLanes);
+    std::vector<float> rtaps((size_t)kResIter * kResLanes * 2);
+    const int left = build_res_lanes(lh, lanes.data(), rtaps.data());
+    if (left < 0) return -1;
+    info[0] = left; info[1] = 0; info[2] = 0; info[3] = 0;
+    for (int w = 0; w < kResLanes / 32; w++) {
+        int per_bank[32] = {0};
+        for (int l = 0; l < 32; l++)
+            if (lanes[32 * w + l].tp_hi >= 0) per_bank[lanes[32 * w + l].base % 32]++;
+        for (int b = 0; b < 32; b++) info[1] = std::max(info[1], per_bank[b]);
+    }
+    const int need = kState + kRdsDown * kResQ + kResLagMax + 1, have = n_in + kState;
+    std::vector<float> sdc((std::max(need, have) + 3) / 4 * 4, NAN);
+    memcpy(sdc.data(), x, sizeof(float) * have);
+    std::vector<int> written(n_out, 0);
+    constexpr int HQ = kResQ / 2;
+    for (int t = 0; t < 2 * kResLanes; t++) {
+        const int tl = t & (kResLanes - 1), qh = t / kResLanes;
+        const ResLane ln = lanes[tl];
+        if (ln.tp_hi < 0) continue;
+        const int lag_hi = ln.lags & 0xFF, lag_lo = (ln.lags >> 8) & 0xFF;
+        const bool has_lo = ln.tp_lo >= 0;
+        const float* xb = sdc.data() + kState + ln.base + kRdsDown * HQ * qh;
+        float aH[HQ], aL[HQ];
+        for (int q = 0; q < HQ; q++) aH[q] = aL[q] = 0.0f;
+        for (int j = 0; j < kResIter; j++) {
+            const float hx = rtaps[((size_t)j * kResLanes + tl) * 2], hy = rtaps[((size_t)j * kResLanes + tl) * 2 + 1];
+            bool vH = true, vL = true;  // the uniform steps do both MACs whatever the lane is
+            if (j < kResLagMax) { vH = j >= lag_hi; vL = has_lo && j >= lag_lo; }
+            if (j >= kResTaps) { vH = j < kResTaps + lag_hi; vL = has_lo && j < kResTaps + lag_lo; }
+            for (int q = 0; q < HQ; q++) {
+                const float xv = xb[kRdsDown * q - j];
+                if (vH) aH[q] = fadd(aH[q], fmul(hx, xv));
+                if (vL) aL[q] = fadd(aL[q], fmul(hy, xv));
+            }
+        }
+        for (int r = 0; r < 2; r++) {
+            const int tp = r ? ln.tp_lo : ln.tp_hi;
+            if (tp < 0) continue;
+            for (int q = 0; q < HQ; q++) {
+                const int n = (HQ * qh + q) * kRdsUp + tp;
+                if (n < n_out) { y[n] = r ? aL[q] : aH[q]; written[n]++; }
+            }
+        }
+    }
+    for (int n = 0; n < n_out; n++) { info[2] += written[n] > 1; info[3] += written[n] == 0; }
+    return 0;
 }
 }
