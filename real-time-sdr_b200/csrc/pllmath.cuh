@@ -634,6 +634,31 @@ SDRB_HD double f2d_pos(float p) {
     return mkd(0x38000000u + (b >> 3), b << 29);
 }
 
+// ---- (float)((double)num / den) for the FM discriminator (/root/reference/src/demod.cpp:11,17) ----
+// The reference divides in double and stores a float; an exact double division costs the FP64 pipe a reciprocal seed and
+// a dozen dependent operations.  Here: q0 = num * rc with rc ~ 1/den good to 2^-21 (a single-precision reciprocal of den's
+// leading bits), one residual and one correction in double (q1 = q0 + (num - q0 den) rc, off by less than 2^-42 q1), and
+// the float rounding of q1 is the reference's unless q1 lies within 2048 double-ulps of a float rounding tie (8e-6 of all
+// quotients) or anything is out of the float-normal range: those return false and the caller divides exactly.
+//   den_approx_f: den (positive, 2^-120 < den < 2^120, checked here) as a float, truncated: one funnel shift and one XOR.
+SDRB_HD bool fm_den_in_range(double den) { return (((dhi(den) >> 20) & 0xFFFu) - (1023u - 120u)) < 240u; }  // sign bit included: negative / NaN / inf fail
+SDRB_HD float fm_den_approx_f(double den) {
+    const uint32_t hi = dhi(den), lo = dlo(den);
+    return bitsf((((hi << 3) | (lo >> 29)) & 0x7FFFFFFFu) ^ 0x40000000u);
+}
+SDRB_HD bool fm_quotient_fast(float num, double den, float rc, float& out) {
+    const double rd = f2d_pos(rc);
+    const double nd = (double)num;
+    const double q0 = dmul(nd, rd);
+    const double e = dfma(-q0, den, nd);
+    const double q1 = dfma(e, rd, q0);
+    const uint32_t E = (dhi(q1) >> 20) & 0x7FFu;                                        // float-normal result: 2^-125 <= |q1| < 2^126
+    const bool range_ok = (E - (1023u - 125u)) < 251u;
+    const bool tie = (((dlo(q1) & 0x1FFFFFFFu) + 2048u) & 0x1FFFF000u) == 0x10000000u;  // low 29 bits in [tie - 2048, tie + 2047]
+    out = (float)q1;
+    return range_ok && !tie;
+}
+
 // v is within 2^kAtanTolLog2 of a float rounding boundary (or too small for the bound to mean anything)
 SDRB_HD bool near_float_boundary_abs(double v) {
     uint64_t b = dbits(v);

@@ -253,4 +253,26 @@ int crh_resampler_lanes(const float* lh, const float* x, int n_in, int n_out, fl
     for (int n = 0; n < n_out; n++) { info[2] += written[n] > 1; info[3] += written[n] == 0; }
     return 0;
 }
+
+// The discriminator's division (fm_quotient_fast) against the exact form (float)((double)num / den),
+// /root/reference/src/demod.cpp:11,17.  num[], I[], Q[]: n operands; den = RN((double)I^2 + (double)Q^2) as the kernel forms
+// it.  The reciprocal seed is the correctly rounded float reciprocal moved by `ulps` float-ulps (the device's
+// rcp.approx is within one).  out[0] = quotients the fast path accepted, out[1] = accepted and different from the exact
+// form (must be 0), out[2] = operands outside the fast path's range.
+void crh_fm_quotient_scan(const float* num, const float* I, const float* Q, int n, int ulps, uint64_t* out) {
+    uint64_t acc = 0, bad = 0, outside = 0;
+    for (int i = 0; i < n; i++) {
+        const double den = dadd(dmul((double)I[i], (double)I[i]), dmul((double)Q[i], (double)Q[i]));
+        const float exact = (float)((double)num[i] / den);
+        if (!fm_den_in_range(den)) { outside++; continue; }
+        const float df = fm_den_approx_f(den);
+        float rc = 1.0f / df;
+        rc = bits2f(f2bits(rc) + (uint32_t)ulps);
+        float got;
+        if (!fm_quotient_fast(num[i], den, rc, got)) continue;
+        acc++;
+        if (f2bits(got) != f2bits(exact)) bad++;
+    }
+    out[0] = acc; out[1] = bad; out[2] = outside;
+}
 }

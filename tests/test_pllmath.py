@@ -269,3 +269,44 @@ def test_phase_detector_error_stays_inside_its_tolerance(host):
         host.crh_head_error(np.ascontiguousarray(th), x, n, out)
         assert out[1] > 0.5 * n
         assert out[0] < 0.4, f"error reaches {out[0]:.2f} of the tolerance (max abs {out[2]:.3e})"
+
+
+def test_discriminator_quotient_fast_path_equals_the_exact_division(host):
+    """cr::fm_quotient_fast (the divide of k_rf_frontend's FM discriminator): whatever it accepts must be
+    (float)((double)num / den) bit for bit (/root/reference/src/demod.cpp:11,17), for a reciprocal seed up to four float-ulps
+    off either way (the device's rcp.approx is within one); it must accept nearly everything in the signal's range and
+    leave the rest (ties, sub-/supernormal operands) to the exact division."""
+    u64p = C.POINTER(C.c_uint64)
+    host.crh_fm_quotient_scan.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, u64p]
+    rng = np.random.default_rng(11)
+    n = 2_000_000
+    sets = []
+    # the chain's own range: |I|, |Q| <= ~1.3, numerators of differences of neighbouring samples
+    I = (rng.standard_normal(n) * 0.5).astype(np.float32)
+    Q = (rng.standard_normal(n) * 0.5).astype(np.float32)
+    sets.append((I * (rng.standard_normal(n) * 0.3).astype(np.float32), I, Q))
+    # every binade the fast path may see, and beyond (it has to decline those)
+    ex = rng.integers(-70, 70, n)
+    I = np.ldexp(rng.uniform(1, 2, n), ex).astype(np.float32) * rng.choice([-1, 1], n).astype(np.float32)
+    Q = np.ldexp(rng.uniform(1, 2, n), ex + rng.integers(-3, 3, n)).astype(np.float32)
+    num = np.ldexp(rng.uniform(1, 2, n), rng.integers(-126, 127, n)).astype(np.float32) * rng.choice([-1, 1], n).astype(np.float32)
+    sets.append((num, I, Q))
+    # quotients that are exactly representable or exact ties in float: small integers over powers of two
+    I = np.ldexp(1.0, rng.integers(-20, 20, n)).astype(np.float32)
+    num = (rng.integers(-(1 << 24), 1 << 24, n).astype(np.float64) * 0.5).astype(np.float32)
+    sets.append((num, I, np.zeros(n, np.float32)))
+    for k, (num, I, Q) in enumerate(sets):
+        for ulps in (0, 1, -1, 4, -4):
+            out = (C.c_uint64 * 3)()
+            host.crh_fm_quotient_scan(np.ascontiguousarray(num), np.ascontiguousarray(I), np.ascontiguousarray(Q), n, ulps, out)
+            accepted, bad, outside = out[0], out[1], out[2]
+            assert bad == 0, (k, ulps, accepted, bad)
+            if k == 0:
+                assert outside < n * 1e-3 and accepted > (n - outside) * 0.9995, (k, ulps, accepted, outside)
+    # specials: zero numerator, infinities and NaN never come out of the fast path wrong (they are declined or exact)
+    num = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, 1.0, 1e-45, 3e38], np.float32)
+    I = np.array([1.0, 1.0, 1.0, 1.0, 1.0, np.inf, np.nan, 1.0, 1e-19], np.float32)
+    Q = np.zeros_like(I)
+    out = (C.c_uint64 * 3)()
+    host.crh_fm_quotient_scan(num, I, Q, num.size, 0, out)
+    assert out[1] == 0
