@@ -81,7 +81,6 @@ struct sdrb_chain {
     int poisoned = 0;        // a launch failed in the middle of a block: the carried state is inconsistent (SDRB_ERR_STATE from then on)
     long long blocks_since_load = 0;  // blocks processed since creation / the last state load: results exist only for those
     int pll_max_ctas = kPllMaxCtas;  // SMs given to k_pll (tuning knob: environment variable SDRB_PLL_MAX_CTAS)
-    int rf_ws_tiles = -1;            // tiles per CTA of k_rf_frontend_ws: -1 automatic, 0 off (SDRB_RF_WS, see launch_rf)
     long long block = 0;  // index of the next block to process
     long long launches = 0;
     cudaStream_t stream = nullptr;  // the caller-visible stream: inputs are ordered on it, joins land on it
@@ -284,23 +283,9 @@ int check_launch(sdrb_chain* c, const char* what, cudaStream_t st) {
     return SDRB_OK;
 }
 
-// Tiles per CTA of the warp-specialised front end (k_rf_frontend_ws): enough CTAs to fill the machine several times over
-// (short tail), enough tiles per CTA for its producer warp to run ahead.  c->rf_ws_tiles: -1 = automatic (four tiles per CTA
-// once there are enough streams; few streams keep one tile per CTA, which has the shorter latency), 0 = off, N = N tiles per
-// CTA whatever the batch (environment variable SDRB_RF_WS, read when the chain is created; tests and measurements).
 template <int DECIM>
 int launch_rf(sdrb_chain* c, const RfArgs& a, cudaStream_t st) {
-    const int tiles = (c->info.if_block + kRfTile - 2) / (kRfTile - 1);
-    if constexpr (DECIM % 2 == 0) {
-        int per_cta = c->rf_ws_tiles;
-        if (per_cta < 0) per_cta = (long long)tiles * c->S >= 4096 ? 4 : 0;
-        if (per_cta > 0 && a.tma_ok) {
-            const int gx = (tiles + per_cta - 1) / per_cta;
-            k_rf_frontend_ws<DECIM><<<dim3(gx, c->S), kRfWsThreads, RfWsLayout<DECIM>::smem, st>>>(c->rf_h, a, tiles);
-            return check_launch(c, "k_rf_frontend_ws", st);
-        }
-    }
-    dim3 grid(tiles, c->S);
+    dim3 grid((c->info.if_block + kRfTile - 2) / (kRfTile - 1), c->S);
     k_rf_frontend<DECIM><<<grid, kRfThreads, 0, st>>>(c->rf_h, a);
     return check_launch(c, "k_rf_frontend", st);
 }
@@ -634,10 +619,6 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         const int v = atoi(e);
         if (v >= 1 && v <= 148) c->pll_max_ctas = v;
     }
-    if (const char* e = getenv("SDRB_RF_WS")) {
-        const int v = atoi(e);
-        if (v >= 0 && v <= 64) c->rf_ws_tiles = v;
-    }
     if (const char* e = getenv("SDRB_GUARD")) c->guard = atoi(e) != 0;
     c->up = cfg->audio_upsample;
     c->down = cfg->audio_decim;
@@ -844,8 +825,6 @@ int sdrb_chain_create(const sdrb_config* cfg, sdrb_chain** out) {
         if (I.rds_block > kResQ * kRdsUp) { sdrb_chain_destroy(c); return fail(SDRB_ERR_INVALID, "RDS block too long for the resampler kernel"); }
         TRYCU(cudaFuncSetAttribute(k_rds_backend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rds_backend_smem(n_if, I.rds_block)));
     }
-    TRYCU(cudaFuncSetAttribute(k_rf_frontend_ws<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RfWsLayout<10>::smem));
-    TRYCU(cudaFuncSetAttribute(k_rf_frontend_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RfWsLayout<4>::smem));
     TRYCU(cudaStreamSynchronize(c->stream));
 #undef TRY
 #undef TRYCU

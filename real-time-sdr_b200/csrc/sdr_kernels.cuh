@@ -207,8 +207,12 @@ __device__ __forceinline__ void fir_bank_core_scalar(const float* __restrict__ s
 // reference's carried prev_I/prev_Q never has to be stored: it is recomputed from the carried input
 // halo (110 IQ pairs, kept as raw bytes; 128 = the byte that unpacks to 0.0f, the initial state).
 // ------------------------------------------------------------------------------------------------
-constexpr int kRfR = 4;
-constexpr int kRfThreads = 64;
+#if !defined(SDRB_RF_R)
+#define SDRB_RF_R 4
+#define SDRB_RF_THREADS 64
+#endif
+constexpr int kRfR = SDRB_RF_R;            // FIR outputs per thread (tools/ab_run.sh variants: -DSDRB_RF_R=2 -DSDRB_RF_THREADS=128)
+constexpr int kRfThreads = SDRB_RF_THREADS;
 constexpr int kRfTile = kRfR * kRfThreads;  // 256 FIR outputs, 255 discriminator outputs
 constexpr int kIqHaloPairs = 112;           // >= kState + max DECIM; 224 bytes, keeps 16-byte alignment
 
@@ -403,151 +407,11 @@ __global__ void __launch_bounds__(kRfThreads) k_rf_frontend(const __grid_constan
     }
 }
 
-// ---- K1, warp-specialised (even DECIM, TMA-able input): a CTA walks over several tiles of its stream.  Warp 0 is the
-// producer: it keeps one bulk copy of raw bytes in flight and unpacks tile t+1 into the other half of a double-buffered
-// float2 tile while warps 1-2 (the same 64-thread MAC loop and discriminator as above) work on tile t, so the FMA pipe no
-// longer idles while a CTA waits for its bytes or unpacks them.  mbarriers: `tma` (bytes landed), full[2] (a tile is
-// unpacked: one arrival by the producer), empty[2] (the consumers are done reading it: 64 arrivals).
-constexpr int kRfWsThreads = 32 + kRfThreads;
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__host__ __device__ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
-
-template <int DECIM>
-struct RfWsLayout {
-    static_assert(DECIM % 2 == 0, "word-at-a-time unpack");
-    static constexpr int L = DECIM * kRfR;
-    static constexpr int NS = DECIM * (kRfTile - 1) + kTaps;
-    static constexpr int NSP = (NS + NS / L + 2 + 1) / 2 * 2;            // float2 slots of one unpacked tile, 16-byte multiple
-    static constexpr int kRawBytes = (2 * NS + 15 + 16) / 16 * 16;
-    static constexpr size_t smem = sizeof(float2) * (2 * NSP + 2 * kRfTile) + kRawBytes;
-};
-
-template <int DECIM>
-__global__ void __launch_bounds__(kRfWsThreads) k_rf_frontend_ws(const __grid_constant__ Taps101 taps, const RfArgs a, const int tiles) {
-    using Y = RfWsLayout<DECIM>;
-    constexpr int L = Y::L, NS = Y::NS, NSP = Y::NSP, kRawBytes = Y::kRawBytes;
-    extern __shared__ __align__(16) uint8_t rfws_smem[];
-    float2* const sxb = reinterpret_cast<float2*>(rfws_smem);         // [2][NSP]
-    float2* const syb = sxb + 2 * NSP;                                // [2][kRfTile] FIR outputs of a tile
-    uint8_t* const raw = reinterpret_cast<uint8_t*>(syb + 2 * kRfTile);
-    __shared__ __align__(8) unsigned long long bar_tma, bar_full[2], bar_empty[2];
-    const int s = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint8_t* blk = a.iq + (size_t)s * a.iq_pitch;
-    const uint8_t* hal = a.halo_in + (size_t)s * (2 * kIqHaloPairs);
-    if (threadIdx.x == 0) {
-        mbar_init(&bar_tma, 1);
-        mbar_init(&bar_full[0], 1);
-        mbar_init(&bar_full[1], 1);
-        mbar_init(&bar_empty[0], kRfThreads);
-        mbar_init(&bar_empty[1], kRfThreads);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // ---------------- producer ----------------
-        auto window = [&](int tile, int& g0, int& A) {
-            g0 = DECIM * (tile * (kRfTile - 1) - 1) - kState;
-            const int byte_lo = 2 * g0;
-            A = (byte_lo >= 0) ? (byte_lo & ~15) : -((-byte_lo + 15) & ~15);
-        };
-        auto issue = [&](int tile) {  // one lane: the tile's bytes (carried halo, then block), widened to 16-byte boundaries
-            int g0, A;
-            window(tile, g0, A);
-            const int byte_hi = min(2 * (g0 + NS), a.row_bytes16);
-            const int lo = max(A, 0);
-            const uint32_t nhalo = A < 0 ? (uint32_t)(-A) : 0u;
-            const uint32_t nblk = byte_hi > lo ? (uint32_t)((byte_hi - lo + 15) & ~15) : 0u;
-            mbar_expect_tx(&bar_tma, nhalo + nblk);
-            if (nhalo) tma_load_1d(raw, hal + (2 * kIqHaloPairs + A), nhalo, &bar_tma);
-            if (nblk) tma_load_1d(raw + (lo - A), blk + lo, nblk, &bar_tma);
-        };
-        // A warp-wide pass over 32 * PER words covers a whole number of padding blocks, so a lane's PER slots repeat from
-        // pass to pass at a constant stride: no index arithmetic in the loop.
-        constexpr int HW = L / 2;                               // words per padding block
-        constexpr int PER = HW / cgcd(32, HW);                  // iterations per period
-        constexpr int WP = 32 * PER;                            // words per period
-        constexpr int SP = 2 * WP + 2 * WP / L;                 // float2 slots per period
-        constexpr int NW = (NS + 1) / 2;                        // words in a tile
-        int off[PER];
-#pragma unroll
-        for (int k = 0; k < PER; k++) off[k] = pad_pos<L>(2 * (lane + 32 * k));
-        if (lane == 0 && (int)blockIdx.x < tiles) issue(blockIdx.x);
-        int k = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, k++) {
-            const int buf = k & 1, use = k >> 1;
-            int g0, A;
-            window(tile, g0, A);
-            mbar_wait(&bar_tma, (uint32_t)(k & 1));
-            if (g0 + NS > a.block_pairs) {  // last tile: bytes past the end of the block become 128, the byte that unpacks to 0.0f
-                for (int o = 2 * a.block_pairs - A + 2 * lane; o < kRawBytes; o += 64) *reinterpret_cast<uint16_t*>(raw + o) = 0x8080u;
-                __syncwarp();
-            }
-            if (use >= 1) mbar_wait(&bar_empty[buf], (uint32_t)((use - 1) & 1));
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw) + ((2 * g0 - A) >> 2);
-            float2* const sx = sxb + buf * NSP;
-            for (int o = 0; o * WP < NW; o++) {
-#pragma unroll
-                for (int kk = 0; kk < PER; kk++) {
-                    const int w = o * WP + 32 * kk + lane;
-                    if (w < NW) {
-                        const uint32_t word = rw[w];
-                        float2* d = sx + off[kk] + o * SP;
-                        d[0] = unpack_iq<0>(word);
-                        d[1] = unpack_iq<1>(word);  // (for odd NS the last one lands in the spare slot past the tile)
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bar_full[buf]);
-                if (tile + (int)gridDim.x < tiles) issue(tile + gridDim.x);  // the raw bytes are consumed: next tile's copy
-            }
-        }
-        return;
-    }
-    // ---------------- consumers ----------------
-    const int ct = threadIdx.x - 32;
-    float* const fm_row = a.fm.cur + (size_t)s * a.fm.pitch;
-    float* const fm_halo = a.fm.nxt + (size_t)s * a.fm.pitch - a.fm.n;
-    const int halo_from = a.fm.n - a.fm.halo;
-    int k = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, k++) {
-        const int buf = k & 1, use = k >> 1;
-        const int m0 = tile * (kRfTile - 1) - 1;
-        if (tile == 0)  // carry the last pairs of this block to the next block's halo
-            for (int i = ct; i < kIqHaloPairs; i += kRfThreads)
-                reinterpret_cast<uint16_t*>(a.halo_out + (size_t)s * (2 * kIqHaloPairs))[i] =
-                    *reinterpret_cast<const uint16_t*>(blk + 2 * (size_t)(a.block_pairs - kIqHaloPairs + i));
-        mbar_wait(&bar_full[buf], (uint32_t)(use & 1));
-        float2 acc[kRfR];
-#pragma unroll
-        for (int j = 0; j < kRfR; j++) acc[j] = make_float2(0.0f, 0.0f);
-        fir_core<DECIM, kRfR, float2>(sxb + buf * NSP + (L + 1) * ct, taps, acc);
-        mbar_arrive(&bar_empty[buf]);
-        float2* const sy = syb + buf * kRfTile;
-#pragma unroll
-        for (int j = 0; j < kRfR; j++) sy[kRfR * ct + j] = acc[j];
-        named_bar_sync(1, kRfThreads);  // (sy[buf] is written again two tiles on, behind the next tile's barrier)
-#pragma unroll
-        for (int i = 0; i < kRfR; i++) {
-            const int q = ct + 1 + i * kRfThreads;
-            const int m = m0 + q;
-            if (q < kRfTile && m < a.if_block) {
-                const float2 c = sy[q], p = sy[q - 1];
-                const float v = fm_discriminate(c.x, c.y, p.x, p.y);
-                fm_row[m] = v;
-                if (m >= halo_from) fm_halo[m] = v;
-                if (a.i_ds) {
-                    a.i_ds[(size_t)s * a.if_block + m] = c.x;
-                    a.q_ds[(size_t)s * a.if_block + m] = c.y;
-                }
-            }
-        }
-    }
-}
+// (A warp-specialised, persistent form of K1 - a producer warp keeping a bulk copy in flight and unpacking tile t+1 while
+// two consumer warps filter tile t, double-buffered float2 tiles, mbarrier hand-off - was built in round 2 and is
+// bit-exact, but slower: 0.205-0.248 ms against 0.167 for 1024 stations with one or two producer warps and 2-15 tiles per
+// CTA (profiles/README.md).  Its 53 KB of shared memory per CTA leave two consumer warps per scheduler, and a MAC loop needs
+// more resident warps than that to keep the FMA pipe busy; the one-tile-per-CTA kernel above has four.)
 
 // ------------------------------------------------------------------------------------------------
 // K2  IF band filters: NF 101-tap FIRs (decim 1) over one input ring, e.g. pilot / stereo / RDS
@@ -1065,8 +929,12 @@ struct AudioArgs {
     float* dc_out;        // optional
 };
 
-constexpr int kAudR = 4;
-constexpr int kAudThreads = 64;
+#if !defined(SDRB_AUD_R)
+#define SDRB_AUD_R 4
+#define SDRB_AUD_THREADS 64
+#endif
+constexpr int kAudR = SDRB_AUD_R;
+constexpr int kAudThreads = SDRB_AUD_THREADS;
 constexpr int kAudTile = kAudR * kAudThreads;
 
 template <int DOWN, bool STEREO>

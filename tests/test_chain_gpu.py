@@ -453,20 +453,3 @@ def test_guard_zones_stay_intact(capi, oracle, station_iq, monkeypatch, mode, ki
     with capi.Chain(mode, kind, n_streams=1) as ch:
         with pytest.raises(capi.SdrError):
             ch.check_guards()
-
-
-@pytest.mark.parametrize("tiles_per_cta,mode,kind,S,overlap", [("1", 0, "r", 2, False), ("3", 0, "r", 5, True), ("4", 1, "s", 3, False),
-                                                               ("64", 0, "m", 2, False), ("4", 2, "m", 3, True)])
-def test_rf_frontend_warp_specialised(capi, oracle, station_iq, monkeypatch, tiles_per_cta, mode, kind, S, overlap):
-    """k_rf_frontend_ws (producer warp: bulk copies + unpack of tile t+1; consumer warps: FIR + discriminator of tile t) is
-    what large batches run; forced here for small ones through SDRB_RF_WS with one tile per CTA, a few, and all of a
-    stream's tiles in one CTA, for both even decimations (10 and 4).  I_ds, Q_ds, fm_demod and everything behind them must
-    equal the oracle, including the first tile (carried halo bytes) and the last (padding behind the block)."""
-    monkeypatch.setenv("SDRB_RF_WS", tiles_per_cta)
-    nblocks = 6
-    stages = [] if overlap else ["I_ds", "Q_ds", "fm_demod"]  # (the stage taps are read block by block: serial mode)
-    iqs = [station_iq(k, mode, nblocks) for k in range(S)]
-    got = run_cuda_chain(capi, mode, kind, iqs, nblocks, stages=stages, overlap=overlap)
-    for s in range(S):
-        want = oracle.chain(mode, kind, iqs[s], stages=stages)
-        _assert_same(got[s], want, ["pcm"] + stages + (RDS_KEYS if kind == "r" else []), f"SDRB_RF_WS={tiles_per_cta} mode {mode} {kind} stream {s}")

@@ -13,6 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_launches_${tag}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_ -s 21 -c 7 -o gpurun_out/prof_${tag} \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_full_${tag}.log 2>&1
+[ -z "${SOAK_BLOCKS:-}" ] || timeout ${SOAK_TIMEOUT:-90} python tools/soak.py --blocks $SOAK_BLOCKS --stations 2 > gpurun_out/soak_${tag}.txt 2> gpurun_out/soak_${tag}.err
 python - gpurun_out/bench_${tag}.json <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
