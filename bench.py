@@ -22,7 +22,8 @@ only torch.distributed traffic is the barrier and the max-over-ranks of the step
   roofline also carries, as scalars the driver's record keeps: bound ("latency": the step is one dependent chain per
          PLL sample), hbm_frac, pll_cycles_per_sample, fir_frac_no_fma / fir_frac_fma_peak (FIR MAC rate against the measured
          unfused multiply+add issue peak / the FMA peak), strong_* (BASELINE configs[4] as written: the 1024 stations SPLIT
-         over the N ranks), capacity_* (4096 stations per GPU: the FIR-bound saturation rate), sustained_* (a >= 5 s run).
+         over the N ranks), capacity_* (4096 stations per GPU: the FIR-bound saturation rate, and capacity_fir_frac_no_fma: the
+         FIR kernels' MAC rate at that batch, kernels serialised), sustained_* (a >= 5 s run).
   e2e    additionally link_gbs (a bare pinned host->device copy of the same size, all ranks at once, device->host running
          the other way) and frac_of_link.
 
@@ -323,8 +324,9 @@ def timed_steps(torch, dist, ch, inputs, pitch, stream, steps, first, world, flu
     return ms
 
 
-def side_run(torch, dist, capi, gen, S, world, local_rank, dev, stream, steps, first_station, inputs=None, n_inputs=4):
-    """A second chain of S stations per rank (strong-scaling split / capacity point): whole-job MS/s and ms per step."""
+def side_run(torch, dist, capi, gen, S, world, local_rank, dev, stream, steps, first_station, inputs=None, n_inputs=4, kernel_blocks=0):
+    """A second chain of S stations per rank (strong-scaling split / capacity point): whole-job MS/s and ms per step;
+    with kernel_blocks > 0 also the per-kernel times of that batch, kernels serialised (median over kernel_blocks blocks)."""
     ch = capi.Chain(CFG["mode"], CFG["kind"], n_streams=S, device=local_rank)
     try:
         bb, bp = ch.info.block_bytes, ch.info.block_pairs
@@ -344,7 +346,23 @@ def side_run(torch, dist, capi, gen, S, world, local_rank, dev, stream, steps, f
             dist.barrier()
         torch.cuda.synchronize()
         ms = timed_steps(torch, dist, ch, inputs, pitch, stream, steps, 6, world, flush)
-        return {"value": world * S * bp * steps / (ms * 1e-3) / 1e6, "ms_per_step": ms / steps, "streams_per_gpu": S}
+        out = {"value": world * S * bp * steps / (ms * 1e-3) / 1e6, "ms_per_step": ms / steps, "streams_per_gpu": S}
+        if kernel_blocks > 0:
+            try:
+                ch.join()
+                torch.cuda.synchronize()
+                ch.set_overlap(False)
+                acc = {}
+                for i in range(kernel_blocks):
+                    ch.set_profiling(True)  # new window per block
+                    ch.process_device(inputs[i % len(inputs)].data_ptr(), pitch)
+                    for k, v in ch.kernel_times().items():
+                        acc.setdefault(k, []).append(v)
+                ch.set_profiling(False)
+                out["kernel_ms_serialised"] = {k: statistics.median(v) for k, v in acc.items()}
+            except Exception as e:  # the side figures never cost the main ones
+                out["kernel_error"] = str(e)[:200]
+        return out
     finally:
         ch.close()
 
@@ -584,10 +602,18 @@ def main():
             roofline.update({"strong_value": round(value, 1), "strong_ms_per_step": round(ms / args.steps, 4),
                              "strong_streams_per_gpu": S, "strong_total_streams": S})
         try:
-            cap = side_run(torch, dist, capi, gen, 4096, world, local_rank, dev, stream, 48, rank * 4096, n_inputs=4)
+            cap = side_run(torch, dist, capi, gen, 4096, world, local_rank, dev, stream, 48, rank * 4096, n_inputs=4, kernel_blocks=4)
             roofline.update({"capacity_streams_per_gpu": 4096, "capacity_value": round(cap["value"], 1),
                              "capacity_ms_per_step": round(cap["ms_per_step"], 4),
                              "capacity_realtime_stations_per_gpu": int(cap["value"] / world / 2.4)})
+            ck = cap.get("kernel_ms_serialised") or {}
+            cap_fir_ms = sum(v for k, v in ck.items() if k in macs)
+            if cap_fir_ms > 0:
+                # the FIR kernels at the batch where they bound the step: the 1024-station figure above includes the partly filled
+                # last wave of the short kernels (2.3 / 3.1 / 1.7 waves of CTAs for audio / carrier filter / RDS back end)
+                roofline.update({"capacity_fir_frac_no_fma": round(4096 * sum(macs.values()) / (cap_fir_ms * 1e-3) / 1e12 / peak_no_fma, 4),
+                                 "capacity_fir_ms_serialised": round(cap_fir_ms, 4),
+                                 "capacity_kernel_ms_serialised": {k: round(v, 4) for k, v in ck.items()}})
         except Exception as e:  # never lose the headline line to the side run
             roofline["capacity_error"] = str(e)[:200]
 
